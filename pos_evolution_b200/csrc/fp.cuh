@@ -1,0 +1,254 @@
+// fp.cuh -- arithmetic in Fp (p = BLS12-381 base field, 381 bits), 12 x 32-bit limbs held in
+// registers, Montgomery form with R = 2^384, values always fully reduced to [0, p).
+//
+// This is kernel K1 of SURVEY.md section 2 (no counterpart in /root/reference: the reference
+// reaches field arithmetic only through its bls.* call sites, pos-evolution.md:165/:736/:976).
+//
+// Montgomery multiplication: word-serial CIOS with two interleaved accumulators.  Products
+// a_j*b_i are 64 bits wide and land on limbs (j, j+1); the six even-j products of a row do
+// not overlap, nor do the six odd-j products, so each half-row is ONE carry chain of
+// mad.lo.cc / madc.hi.cc pairs (ptxas: IMAD.WIDE.U32 with predicate carry).  `ev` collects
+// the chain aligned at limb 0, `od` the chain aligned at limb 1; the two chains are
+// data-independent, which gives the integer pipe two instructions in flight per thread.
+// After the reduction step ev[0] == 0 and the division by 2^32 is a change of roles: the
+// old `od` becomes the limb-0 accumulator and the old `ev`, shifted down by two limbs while
+// the next row is accumulated into it, becomes the limb-1 accumulator.
+#pragma once
+#include "consts.cuh"
+
+namespace b2 {
+
+struct fp {
+    uint32_t l[12];
+};
+
+HD fp fp_load_const(int off) {
+    fp r;
+    const uint32_t* t = const_table() + off;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = t[i];
+    return r;
+}
+HD fp fp_zero() {
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = 0;
+    return r;
+}
+HD fp fp_one() { return fp_load_const(C_ONE); }
+
+HD bool fp_is_zero(const fp& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) o |= a.l[i];
+    return o == 0;
+}
+HD bool fp_eq(const fp& a, const fp& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) o |= a.l[i] ^ b.l[i];
+    return o == 0;
+}
+// branch-free select: c ? a : b
+HD fp fp_select(bool c, const fp& a, const fp& b) {
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+
+// r = (t >= p) ? t - p : t     for t < 2p
+HD void fp_final_sub(uint32_t* t) {
+    uint32_t d[12];
+    d[0] = sub_cc(t[0], P_LIMB(0));
+#pragma unroll
+    for (int i = 1; i < 12; i++) d[i] = subc_cc(t[i], P_LIMB(i));
+    uint32_t borrow = subc(0, 0);               // 0xffffffff when t < p
+#pragma unroll
+    for (int i = 0; i < 12; i++) t[i] = borrow ? t[i] : d[i];
+}
+
+HD fp fp_add(const fp& a, const fp& b) {
+    fp r;
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    fp_final_sub(r.l);                          // a + b < 2p < 2^384: no carry out
+    return r;
+}
+
+HD fp fp_sub(const fp& a, const fp& b) {
+    fp r;
+    r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+    uint32_t m = subc(0, 0);                    // all-ones when a < b
+    r.l[0] = add_cc(r.l[0], P_LIMB(0) & m);
+#pragma unroll
+    for (int i = 1; i < 12; i++) r.l[i] = addc_cc(r.l[i], P_LIMB(i) & m);
+    return r;
+}
+
+HD fp fp_neg(const fp& a) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) nz |= a.l[i];
+    uint32_t m = nz ? 0xffffffffu : 0u;
+    fp r;
+    r.l[0] = sub_cc(P_LIMB(0) & m, a.l[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) r.l[i] = subc_cc(P_LIMB(i) & m, a.l[i]);
+    return r;
+}
+
+HD fp fp_dbl(const fp& a) { return fp_add(a, a); }
+
+// one reduction step: m = E[0]*(-p^-1); (E, O) += m*p; afterwards E[0] == 0
+HD void mont_reduce_row(uint32_t* E, uint32_t* O) {
+    uint32_t m = E[0] * B2_MONT_INV;
+    mad_wide_cc(O[0], O[1], P_LIMB(1), m);
+#pragma unroll
+    for (int k = 2; k < 12; k += 2) madc_wide_cc(O[k], O[k + 1], P_LIMB(k + 1), m);
+    // no carry out of O: the running total is < 2^416 (see header)
+    mad_wide_cc(E[0], E[1], P_LIMB(0), m);
+#pragma unroll
+    for (int j = 2; j < 12; j += 2) madc_wide_cc(E[j], E[j + 1], P_LIMB(j), m);
+    O[11] = addc(O[11], 0);                     // E's carry out lands on limb 12 = O[11]
+}
+
+// accumulate row a*bi.  E: accumulator aligned at limb 0 (the previous row's odd accumulator);
+// X: the previous even accumulator (X[0] == 0), rewritten in place as the new odd accumulator.
+HD void mont_mul_row(uint32_t* E, uint32_t* X, const uint32_t* a, uint32_t bi) {
+    E[0] = add_cc(E[0], X[1]);                  // old limb 1 -> new limb 0; carry goes to new limb 1 = X'[0]
+#pragma unroll
+    for (int k = 0; k < 12; k += 2)
+        madc_wide_cc_from(X[k], X[k + 1], a[k + 1], bi, (k + 2 < 12) ? X[k + 2] : 0u, (k + 3 < 12) ? X[k + 3] : 0u);
+    // hi(a*b) <= 2^32-2: the final +carry cannot overflow
+    mad_wide_cc(E[0], E[1], a[0], bi);
+#pragma unroll
+    for (int j = 2; j < 12; j += 2) madc_wide_cc(E[j], E[j + 1], a[j], bi);
+    X[11] = addc(X[11], 0);
+}
+
+HD fp fp_mul(const fp& a, const fp& b) {
+    uint32_t ev[12], od[12];
+    const uint32_t b0 = b.l[0];
+#pragma unroll
+    for (int j = 0; j < 12; j += 2) {
+        mul_wide(ev[j], ev[j + 1], a.l[j], b0);
+        mul_wide(od[j], od[j + 1], a.l[j + 1], b0);
+    }
+    mont_reduce_row(ev, od);
+#pragma unroll
+    for (int i = 1; i < 12; i += 2) {
+        mont_mul_row(od, ev, a.l, b.l[i]);      // roles swap every row
+        mont_reduce_row(od, ev);
+        if (i + 1 < 12) {
+            mont_mul_row(ev, od, a.l, b.l[i + 1]);
+            mont_reduce_row(ev, od);
+        }
+    }
+    // last row (i = 11) used E = od, O = ev:  T/2^32 = (od >> 32) + ev
+    fp r;
+    r.l[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < 11; k++) r.l[k] = addc_cc(ev[k], od[k + 1]);
+    r.l[11] = addc(ev[11], 0);
+    fp_final_sub(r.l);
+    return r;
+}
+
+HD fp fp_sqr(const fp& a) { return fp_mul(a, a); }
+
+// canonical <-> Montgomery
+HD fp fp_to_mont(const fp& a) { return fp_mul(a, fp_load_const(C_R2)); }
+HD fp fp_from_mont(const fp& a) {
+    fp one = fp_zero();
+    one.l[0] = 1;
+    return fp_mul(a, one);
+}
+
+// small multiples
+HD fp fp_mul3(const fp& a) { return fp_add(fp_dbl(a), a); }
+HD fp fp_mul4(const fp& a) { return fp_dbl(fp_dbl(a)); }
+HD fp fp_mul8(const fp& a) { return fp_dbl(fp_mul4(a)); }
+
+// a^e for a 384-bit exponent stored canonically in the constant table at `off` (uniform across
+// threads, so the bit tests do not diverge).  Fixed 4-bit window, 96 windows.
+HD fp fp_pow_const(const fp& a, int off) {
+    fp tbl[16];
+    tbl[0] = fp_one();
+    tbl[1] = a;
+#pragma unroll 1
+    for (int i = 2; i < 16; i++) tbl[i] = fp_mul(tbl[i - 1], a);
+    const uint32_t* e = const_table() + off;
+    fp r = fp_one();
+    bool started = false;
+#pragma unroll 1
+    for (int w = 95; w >= 0; w--) {
+        uint32_t nib = (e[w >> 3] >> ((w & 7) * 4)) & 15u;
+        if (started) {
+            r = fp_sqr(r);
+            r = fp_sqr(r);
+            r = fp_sqr(r);
+            r = fp_sqr(r);
+        }
+        if (nib) {
+            r = started ? fp_mul(r, tbl[nib]) : tbl[nib];
+            started = true;
+        }
+    }
+    return r;
+}
+
+HD fp fp_inv(const fp& a) { return fp_pow_const(a, C_EXP_PM2); }        // 0 -> 0
+
+// d = a^((p-3)/4).  Then a*d = a^((p+1)/4) is the square-root candidate and, when a is a
+// non-zero square, d = 1/sqrt(a).
+HD fp fp_pow_pm3d4(const fp& a) { return fp_pow_const(a, C_EXP_PM3D4); }
+
+// sqrt in Fp: returns true and writes a root when `a` is a square
+HD bool fp_sqrt(const fp& a, fp& root) {
+    fp d = fp_pow_pm3d4(a);
+    root = fp_mul(d, a);
+    return fp_eq(fp_sqr(root), a);
+}
+
+// "lexicographically largest" test on the canonical value: a > (p-1)/2
+HD bool fp_is_lex_large_canonical(const fp& canon) {
+    const uint32_t* h = const_table() + C_HALF_P;
+    uint32_t t = sub_cc(h[0], canon.l[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) t = subc_cc(h[i], canon.l[i]);
+    (void)t;
+    return subc(0, 0) != 0;                     // borrow <=> half_p < a
+}
+
+// big-endian 48-byte encoding <-> canonical limbs
+HD void fp_to_be48(const fp& canon, uint8_t* out) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint32_t w = canon.l[11 - i];
+        out[4 * i + 0] = (uint8_t)(w >> 24);
+        out[4 * i + 1] = (uint8_t)(w >> 16);
+        out[4 * i + 2] = (uint8_t)(w >> 8);
+        out[4 * i + 3] = (uint8_t)w;
+    }
+}
+HD fp fp_from_be48(const uint8_t* in) {
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+        r.l[11 - i] = ((uint32_t)in[4 * i] << 24) | ((uint32_t)in[4 * i + 1] << 16) | ((uint32_t)in[4 * i + 2] << 8) | in[4 * i + 3];
+    return r;
+}
+// canonical value < p ?
+HD bool fp_canonical_lt_p(const fp& canon) {
+    uint32_t t = sub_cc(canon.l[0], P_LIMB(0));
+#pragma unroll
+    for (int i = 1; i < 12; i++) t = subc_cc(canon.l[i], P_LIMB(i));
+    (void)t;
+    return subc(0, 0) != 0;
+}
+
+}  // namespace b2
