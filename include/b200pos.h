@@ -1,0 +1,130 @@
+/* b200pos.h -- C ABI of libb200pos.so: B200-native attestation aggregation + LMD-GHOST fork choice.
+ *
+ * Drop-in boundary for the hot path of /root/reference/pos-evolution.md
+ *     process_attestation (:722) -> bls.Aggregate / FastAggregateVerify -> get_head (:1102)
+ * The reference is executable Python (pyspec) and has no FFI of its own; the functions below are
+ * what a ctypes binding behind the pyspec names would call (INTEGRATION.md shows the stub).
+ * Each entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; the caller owns every buffer; the library keeps only the
+ *     registry / block-tree / latest-message tables it allocated on the device.
+ *   - return value: 0 = ok, negative = B2_E* (environment / argument errors).  Cryptographic
+ *     invalidity is DATA (ok_out[i] = 0, seg_status[i] != 0), never an error code.  On error no
+ *     output buffer and no device table is modified (pos-evolution.md:1041).
+ *   - functions without the _dev suffix take HOST pointers, are synchronous and do their own
+ *     host<->device copies.  *_dev functions take DEVICE pointers plus a cudaStream_t (as void*)
+ *     and only enqueue work (used by bench.py and by the multi-GPU path, where the u64 vote
+ *     weights are all-reduced by NCCL between b2_vote_weights_dev and b2_head_from_votes_dev).
+ *   - a b2_ctx is bound to one GPU and is not thread-safe (pyspec is single-threaded).
+ *   - there is no CPU fallback: b2_init fails with B2_ENODEVICE when no sm_100 GPU is present.
+ */
+#ifndef B200POS_H
+#define B200POS_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_ctx b2_ctx;
+
+enum {
+    B2_OK = 0,
+    B2_EINVAL = -1,    /* bad argument (null pointer, index out of range, missing table) */
+    B2_ECUDA = -2,     /* CUDA runtime error; b2_last_error() has the text */
+    B2_ENODEVICE = -3, /* no usable GPU */
+    B2_ENOMEM = -4
+};
+
+/* status bits written by b2_g1_aggregate (why py_ecc's FastAggregateVerify would return False) */
+enum { B2_PK_OK = 0, B2_PK_INVALID_KEY = 1, B2_PK_EMPTY = 2, B2_PK_INFINITY = 4 };
+
+int b2_init(int device, b2_ctx** out);
+void b2_destroy(b2_ctx* ctx);
+const char* b2_last_error(b2_ctx* ctx);
+int b2_sync(b2_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t b2_launch_count(b2_ctx* ctx);
+
+/* ---- validator registry: BeaconState.validators[*].{pubkey, effective_balance} (pos-evolution.md:36-45, :354).
+ * Decompresses and KeyValidates every pubkey ONCE (py_ecc does it on every FastAggregateVerify call) and
+ * keeps 96-byte affine Montgomery records on the device.  flags: bit0 = active at the fork-choice epoch
+ * (is_active_validator), bit1 = slashed.  pk_valid_out (may be NULL): 1 = KeyValidate passed. */
+int b2_registry_load(b2_ctx* ctx, const uint8_t* pk48, const uint64_t* effective_balance, const uint8_t* flags,
+                     uint64_t n_validators, uint8_t* pk_valid_out);
+/* refresh balances / flags only (process_effective_balance_updates, pos-evolution.md:122-133, changes them per epoch) */
+int b2_registry_update_balances(b2_ctx* ctx, const uint64_t* effective_balance, const uint8_t* flags, uint64_t n_validators);
+
+/* ---- committees and aggregation bits (get_beacon_committee :729, get_attesting_indices :745):
+ * aggregate a has members[off[a] .. off[a+1]) (validator indices, committee order) and bit j of
+ * bits[a*bits_stride ...] (little-endian within bytes, SSZ Bitlist order) selects member j. */
+
+/* K2: per aggregate, sum of the selected pubkeys; out48 = compressed G1 (infinity encoding when empty). */
+int b2_g1_aggregate(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
+                    uint32_t n_agg, uint8_t* out48, uint8_t* status);
+
+/* bls.Aggregate (eth2spec.utils.bls; named by BASELINE.json, called as get_aggregate_signature upstream), batched:
+ * segment s = signatures [seg_off[s], seg_off[s+1]).  seg_status: 0 ok, 1 = a signature is undecodable
+ * (py_ecc raises), 2 = empty segment (py_ecc raises).  No subgroup check, as in py_ecc. */
+int b2_aggregate(b2_ctx* ctx, const uint8_t* sig96, const uint32_t* seg_off, uint32_t n_seg, uint8_t* out96, int32_t* seg_status);
+
+/* bls.FastAggregateVerify inside is_valid_indexed_attestation (pos-evolution.md:736, :976), batched over
+ * aggregates, pubkeys taken from the registry by index.  ok_out[a] in {0,1}; never an error for bad crypto. */
+int b2_fast_aggregate_verify(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
+                             const uint8_t* msg32, const uint8_t* sig96, uint32_t n_agg, uint8_t* ok_out);
+
+/* pyspec-literal form: explicit compressed pubkeys, aggregate a uses pk48[pk_off[a] .. pk_off[a+1]).
+ * Decompresses + KeyValidates every key on every call (what py_ecc does).  bls.Verify (:165) is the 1-key case. */
+int b2_fast_aggregate_verify_pks(b2_ctx* ctx, const uint8_t* pk48, const uint32_t* pk_off, const uint8_t* msg32,
+                                 const uint8_t* sig96, uint32_t n_agg, uint8_t* ok_out);
+
+/* bls.SkToPk / bls.Sign, batched (sk = 8 little-endian u32 limbs, 0 < sk < r).  Signature i = sk[i] * H(msg[msg_idx[i]]). */
+int b2_sk_to_pk(b2_ctx* ctx, const uint32_t* sk8, uint64_t n, uint8_t* pk48_out);
+int b2_sign(b2_ctx* ctx, const uint32_t* sk8, const uint32_t* msg_idx, uint64_t n, const uint8_t* msg32, uint32_t n_msg,
+            uint8_t* sig96_out);
+/* H(m) compressed, for tests (hash_to_G2 with the POP ciphersuite tag) */
+int b2_hash_to_g2(b2_ctx* ctx, const uint8_t* msg32, uint32_t n_msg, uint8_t* out96);
+
+/* ---- fork choice --------------------------------------------------------------------------------
+ * Store.latest_messages (pos-evolution.md:901) lives on the device as (epoch, block index) per validator. */
+int b2_latest_messages_reset(b2_ctx* ctx);
+/* bulk load: has_msg[v] != 0 -> (epoch[v], block_idx[v]); equivocating[v] != 0 -> Store.equivocating_indices (:897) */
+int b2_latest_messages_load(b2_ctx* ctx, const uint64_t* epoch, const uint32_t* block_idx, const uint8_t* has_msg,
+                            const uint8_t* equivocating, uint64_t n_validators);
+int b2_latest_messages_read(b2_ctx* ctx, uint64_t* epoch, uint32_t* block_idx, uint8_t* has_msg, uint64_t n_validators);
+/* update_latest_messages (pos-evolution.md:1435-1441) for a batch of attestations in list order:
+ * for each accepted aggregate a (accept[a] != 0, or accept == NULL) and each selected member i not equivocating:
+ * set (target_epoch[a], block_idx[a]) iff i has no message or target_epoch[a] > stored epoch.  Order-exact. */
+int b2_latest_messages_update(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
+                              const uint64_t* target_epoch, const uint32_t* block_idx, const uint8_t* accept, uint32_t n_agg);
+
+/* Store.blocks (pos-evolution.md:898) as arrays in topological order (parent[b] < b, parent[0] ignored; block 0 =
+ * store.justified_checkpoint.root).  leaf_viable[b]: the get_filtered_block_tree leaf test (:1104, prose :1121-1124). */
+int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, const uint8_t* root32, const uint8_t* leaf_viable,
+                 uint32_t n_blocks);
+/* get_latest_attesting_balance == get_weight (called at pos-evolution.md:1116) for EVERY block; boost_idx < 0: no boost */
+int b2_get_weights(b2_ctx* ctx, int32_t boost_idx, uint64_t boost_score, uint64_t* weight_out);
+/* get_head (pos-evolution.md:1102-1116): index of the head block */
+int b2_get_head(b2_ctx* ctx, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score, uint32_t* head_idx_out);
+
+/* ---- device-pointer entry points (asynchronous on `stream`) ------------------------------------------------------ */
+int b2_aggregate_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig, uint8_t* d_out96,
+                     int32_t* d_seg_status, void* stream);
+int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
+                                 uint32_t bits_stride, const uint8_t* d_msg32, const uint8_t* d_sig96, uint32_t n_agg,
+                                 uint8_t* d_ok_out, void* stream);
+int b2_latest_messages_update_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
+                                  uint32_t bits_stride, const uint64_t* d_target_epoch, const uint32_t* d_block_idx,
+                                  const uint8_t* d_accept, uint32_t n_agg, void* stream);
+/* direct (un-propagated) vote weight per block in tree pre-order, u64[n_blocks]: the quantity that is summed across
+ * GPUs (ncclAllReduce sum, u64) when validators are sharded; then b2_head_from_votes_dev finishes on every rank. */
+int b2_vote_weights_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, void* stream);
+int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
+                           uint64_t* d_weight_out /* may be NULL */, uint32_t* d_head_idx_out, void* stream);
+uint32_t b2_tree_size(b2_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200POS_H */

@@ -1,0 +1,653 @@
+// b200pos.cu -- C ABI (include/b200pos.h) over the kernels in kernels.cuh.  Single translation
+// unit -> libb200pos.so (nvcc -gencode arch=compute_100a,code=sm_100a).  No CPU fallback anywhere.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/b200pos.h"
+#include "kernels.cuh"
+
+using namespace b2;
+
+struct dbuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct b2_ctx {
+    int device = 0;
+    cudaStream_t s_main = nullptr, s_aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    char err[512] = {0};
+    uint64_t launches = 0;
+    // registry
+    uint64_t n_val = 0;
+    uint32_t* d_records = nullptr;
+    uint8_t* d_valid = nullptr;
+    uint64_t* d_eff = nullptr;
+    uint8_t* d_flags = nullptr;
+    // latest messages
+    unsigned long long* d_lmd_key = nullptr;
+    uint32_t* d_lmd_block = nullptr;
+    uint8_t* d_equiv = nullptr;
+    // block tree
+    uint32_t n_blocks = 0;
+    uint32_t *d_pre = nullptr, *d_size = nullptr, *d_child_off = nullptr, *d_child_idx = nullptr, *d_rank = nullptr, *d_next = nullptr;
+    uint8_t* d_keep = nullptr;
+    unsigned long long *d_votes = nullptr, *d_prefix = nullptr, *d_weight = nullptr;
+    uint32_t* d_head = nullptr;
+    // scratch
+    dbuf sc_pkjac, sc_pkst, sc_haff, sc_hflag, sc_saff, sc_sflag, sc_f, sc_g2aff, sc_g2st, sc_rec, sc_val;
+    dbuf in_a, in_b, in_c, in_d, in_e, in_f, in_g, out_a, out_b;
+};
+
+static int fail_cuda(b2_ctx* c, cudaError_t e, const char* what) {
+    if (c) snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+    return B2_ECUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);   \
+    } while (0)
+#define CKL(ctx_)                                                          \
+    do {                                                                   \
+        cudaError_t e_ = cudaGetLastError();                               \
+        if (e_ != cudaSuccess) return fail_cuda(ctx_, e_, "kernel launch"); \
+        (ctx_)->launches++;                                                \
+    } while (0)
+#define REQUIRE(cond, msg)                                         \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", msg); \
+            return B2_EINVAL;                                      \
+        }                                                          \
+    } while (0)
+
+static int ensure(b2_ctx* ctx, dbuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return B2_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = std::max<size_t>(bytes, 256);
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return B2_OK;
+}
+template <class T> static int dev_alloc(b2_ctx* ctx, T** p, size_t count) {
+    if (*p) {
+        CK(cudaFree(*p));
+        *p = nullptr;
+    }
+    CK(cudaMalloc((void**)p, std::max<size_t>(count * sizeof(T), 256)));
+    return B2_OK;
+}
+static inline unsigned blocks_for(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+extern "C" {
+
+int b2_init(int device, b2_ctx** out) {
+    if (!out) return B2_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return B2_ENODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B2_ENODEVICE;
+    if (prop.major < 10) return B2_ENODEVICE;      // sm_100a cubin only
+    b2_ctx* ctx = new (std::nothrow) b2_ctx();
+    if (!ctx) return B2_ENOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return B2_ENODEVICE;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->s_aux[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return B2_ECUDA;
+    }
+    *out = ctx;
+    return B2_OK;
+}
+
+void b2_destroy(b2_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {ctx->d_records, ctx->d_valid, ctx->d_eff, ctx->d_flags, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_pre,
+                    ctx->d_size, ctx->d_child_off, ctx->d_child_idx, ctx->d_rank, ctx->d_next, ctx->d_keep, ctx->d_votes, ctx->d_prefix,
+                    ctx->d_weight, ctx->d_head};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    dbuf* bufs[] = {&ctx->sc_pkjac, &ctx->sc_pkst, &ctx->sc_haff, &ctx->sc_hflag, &ctx->sc_saff, &ctx->sc_sflag, &ctx->sc_f,
+                    &ctx->sc_g2aff, &ctx->sc_g2st, &ctx->sc_rec, &ctx->sc_val, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d,
+                    &ctx->in_e, &ctx->in_f, &ctx->in_g, &ctx->out_a, &ctx->out_b};
+    for (dbuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    delete ctx;
+}
+
+const char* b2_last_error(b2_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+uint64_t b2_launch_count(b2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint32_t b2_tree_size(b2_ctx* ctx) { return ctx ? ctx->n_blocks : 0; }
+int b2_sync(b2_ctx* ctx) {
+    REQUIRE(ctx, "null context");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ registry
+int b2_registry_load(b2_ctx* ctx, const uint8_t* pk48, const uint64_t* eff, const uint8_t* flags, uint64_t n, uint8_t* pk_valid_out) {
+    REQUIRE(ctx && pk48 && eff && flags && n > 0 && n < (1ull << 32), "registry_load: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_records, n * 24)) || (rc = dev_alloc(ctx, &ctx->d_valid, n)) || (rc = dev_alloc(ctx, &ctx->d_eff, n)) ||
+        (rc = dev_alloc(ctx, &ctx->d_flags, n)) || (rc = dev_alloc(ctx, &ctx->d_lmd_key, n)) || (rc = dev_alloc(ctx, &ctx->d_lmd_block, n)) ||
+        (rc = dev_alloc(ctx, &ctx->d_equiv, n)))
+        return rc;
+    if ((rc = ensure(ctx, ctx->in_a, n * 48))) return rc;
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpyAsync(ctx->in_a.p, pk48, n * 48, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_eff, eff, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_flags, flags, n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->d_lmd_key, 0, n * 8, s));
+    CK(cudaMemsetAsync(ctx->d_lmd_block, 0, n * 4, s));
+    CK(cudaMemsetAsync(ctx->d_equiv, 0, n, s));
+    k_registry_load<<<blocks_for(n, 128), 128, 0, s>>>((const uint8_t*)ctx->in_a.p, n, ctx->d_records, ctx->d_valid);
+    CKL(ctx);
+    if (pk_valid_out) CK(cudaMemcpyAsync(pk_valid_out, ctx->d_valid, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->n_val = n;
+    return B2_OK;
+}
+
+int b2_registry_update_balances(b2_ctx* ctx, const uint64_t* eff, const uint8_t* flags, uint64_t n) {
+    REQUIRE(ctx && eff && flags && n == ctx->n_val && n > 0, "registry_update_balances: registry not loaded or size mismatch");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_eff, eff, n * 8, cudaMemcpyHostToDevice, ctx->s_main));
+    CK(cudaMemcpyAsync(ctx->d_flags, flags, n, cudaMemcpyHostToDevice, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    return B2_OK;
+}
+
+// host-side validation of a committee batch (indices must address the registry)
+static int check_batch(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, uint32_t bits_stride, uint32_t n_agg, uint64_t limit) {
+    REQUIRE(off[0] == 0, "off[0] must be 0");
+    for (uint32_t a = 0; a < n_agg; a++) {
+        REQUIRE(off[a + 1] >= off[a], "off must be non-decreasing");
+        REQUIRE((uint64_t)(off[a + 1] - off[a]) <= (uint64_t)bits_stride * 8, "committee larger than bits_stride*8");
+    }
+    const uint32_t total = off[n_agg];
+    for (uint32_t i = 0; i < total; i++) REQUIRE(members[i] < limit, "member index outside the registry");
+    return B2_OK;
+}
+
+// upload members/off/bits into in_a/in_b/in_c
+static int upload_batch(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride, uint32_t n_agg,
+                        cudaStream_t s) {
+    int rc;
+    const uint32_t total = off[n_agg];
+    if ((rc = ensure(ctx, ctx->in_a, (size_t)total * 4 + 4)) || (rc = ensure(ctx, ctx->in_b, (size_t)(n_agg + 1) * 4)) ||
+        (rc = ensure(ctx, ctx->in_c, (size_t)n_agg * bits_stride + 16)))
+        return rc;
+    if (total) CK(cudaMemcpyAsync(ctx->in_a.p, members, (size_t)total * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_b.p, off, (size_t)(n_agg + 1) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_c.p, bits, (size_t)n_agg * bits_stride, cudaMemcpyHostToDevice, s));
+    return B2_OK;
+}
+
+static int g1_aggregate_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
+                            uint32_t n_agg, cudaStream_t s) {
+    int rc;
+    if ((rc = ensure(ctx, ctx->sc_pkjac, (size_t)n_agg * 144)) || (rc = ensure(ctx, ctx->sc_pkst, n_agg))) return rc;
+    k_g1_aggregate<<<n_agg, 128, 0, s>>>(ctx->d_records, ctx->d_valid, d_members, d_off, d_bits, bits_stride, n_agg,
+                                         (uint32_t*)ctx->sc_pkjac.p, (uint8_t*)ctx->sc_pkst.p);
+    CKL(ctx);
+    return B2_OK;
+}
+
+int b2_g1_aggregate(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride, uint32_t n_agg,
+                    uint8_t* out48, uint8_t* status) {
+    REQUIRE(ctx && members && off && bits && out48 && status && n_agg > 0 && bits_stride > 0, "g1_aggregate: bad arguments");
+    REQUIRE(ctx->n_val > 0, "g1_aggregate: registry not loaded");
+    int rc;
+    if ((rc = check_batch(ctx, members, off, bits_stride, n_agg, ctx->n_val))) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    if ((rc = upload_batch(ctx, members, off, bits, bits_stride, n_agg, s))) return rc;
+    if ((rc = g1_aggregate_dev(ctx, (const uint32_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, (const uint8_t*)ctx->in_c.p, bits_stride, n_agg, s)))
+        return rc;
+    if ((rc = ensure(ctx, ctx->out_a, (size_t)n_agg * 48))) return rc;
+    k_g1_compress<<<blocks_for(n_agg, 64), 64, 0, s>>>((const uint32_t*)ctx->sc_pkjac.p, n_agg, (uint8_t*)ctx->out_a.p);
+    CKL(ctx);
+    std::vector<uint8_t> t48((size_t)n_agg * 48), tst(n_agg);
+    CK(cudaMemcpyAsync(t48.data(), ctx->out_a.p, t48.size(), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(tst.data(), ctx->sc_pkst.p, n_agg, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(out48, t48.data(), t48.size());
+    memcpy(status, tst.data(), n_agg);
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ bls.Aggregate
+int b2_aggregate_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig, uint8_t* d_out96,
+                     int32_t* d_seg_status, void* stream) {
+    REQUIRE(ctx && d_seg_off && d_out96 && d_seg_status && n_seg > 0 && (n_sig == 0 || d_sig96), "aggregate_dev: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure(ctx, ctx->sc_g2aff, (size_t)n_sig * 192 + 16)) || (rc = ensure(ctx, ctx->sc_g2st, n_sig + 16))) return rc;
+    if (n_sig) {
+        k_g2_decompress<<<blocks_for(n_sig, 128), 128, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p);
+        CKL(ctx);
+    }
+    k_g2_segment_sum<<<n_seg, 128, 0, s>>>((const uint32_t*)ctx->sc_g2aff.p, (const uint8_t*)ctx->sc_g2st.p, d_seg_off, n_seg, d_out96, d_seg_status);
+    CKL(ctx);
+    return B2_OK;
+}
+
+int b2_aggregate(b2_ctx* ctx, const uint8_t* sig96, const uint32_t* seg_off, uint32_t n_seg, uint8_t* out96, int32_t* seg_status) {
+    REQUIRE(ctx && seg_off && out96 && seg_status && n_seg > 0, "aggregate: bad arguments");
+    REQUIRE(seg_off[0] == 0, "aggregate: seg_off[0] must be 0");
+    for (uint32_t s = 0; s < n_seg; s++) REQUIRE(seg_off[s + 1] >= seg_off[s], "aggregate: seg_off must be non-decreasing");
+    const uint64_t n_sig = seg_off[n_seg];
+    REQUIRE(n_sig == 0 || sig96, "aggregate: null signatures");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_d, n_sig * 96 + 16)) || (rc = ensure(ctx, ctx->in_b, (size_t)(n_seg + 1) * 4)) ||
+        (rc = ensure(ctx, ctx->out_a, (size_t)n_seg * 96)) || (rc = ensure(ctx, ctx->out_b, (size_t)n_seg * 4)))
+        return rc;
+    if (n_sig) CK(cudaMemcpyAsync(ctx->in_d.p, sig96, n_sig * 96, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_b.p, seg_off, (size_t)(n_seg + 1) * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = b2_aggregate_dev(ctx, (const uint8_t*)ctx->in_d.p, (const uint32_t*)ctx->in_b.p, n_seg, n_sig, (uint8_t*)ctx->out_a.p,
+                               (int32_t*)ctx->out_b.p, s)))
+        return rc;
+    std::vector<uint8_t> t96((size_t)n_seg * 96);
+    std::vector<int32_t> tst(n_seg);
+    CK(cudaMemcpyAsync(t96.data(), ctx->out_a.p, t96.size(), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(tst.data(), ctx->out_b.p, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(out96, t96.data(), t96.size());
+    memcpy(seg_status, tst.data(), (size_t)n_seg * 4);
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ FastAggregateVerify
+// Given aggregated pubkeys in sc_pkjac / sc_pkst: hash, signature check, two Miller loops, final exp.
+// H(m) and the signature check do not depend on the pubkey aggregation: they run on two side
+// streams while the caller's stream aggregates, then join for the pairing.
+static int verify_tail(b2_ctx* ctx, const uint8_t* d_msg32, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s, bool fork_done) {
+    int rc;
+    if ((rc = ensure(ctx, ctx->sc_haff, (size_t)n_agg * 192)) || (rc = ensure(ctx, ctx->sc_hflag, n_agg)) ||
+        (rc = ensure(ctx, ctx->sc_saff, (size_t)n_agg * 192)) || (rc = ensure(ctx, ctx->sc_sflag, n_agg)) ||
+        (rc = ensure(ctx, ctx->sc_f, (size_t)n_agg * 2 * 576)))
+        return rc;
+    (void)fork_done;
+    CK(cudaEventRecord(ctx->ev_fork, s));
+    CK(cudaStreamWaitEvent(ctx->s_aux[0], ctx->ev_fork, 0));
+    CK(cudaStreamWaitEvent(ctx->s_aux[1], ctx->ev_fork, 0));
+    k_hash_to_g2<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->sc_hflag.p);
+    CKL(ctx);
+    k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[1]>>>(d_sig96, n_agg, (uint32_t*)ctx->sc_saff.p, (uint8_t*)ctx->sc_sflag.p);
+    CKL(ctx);
+    CK(cudaEventRecord(ctx->ev_join[0], ctx->s_aux[0]));
+    CK(cudaEventRecord(ctx->ev_join[1], ctx->s_aux[1]));
+    return B2_OK;
+}
+static int verify_join(b2_ctx* ctx, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s) {
+    CK(cudaStreamWaitEvent(s, ctx->ev_join[0], 0));
+    CK(cudaStreamWaitEvent(s, ctx->ev_join[1], 0));
+    k_miller<<<blocks_for(2ull * n_agg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_pkjac.p, (const uint8_t*)ctx->sc_pkst.p,
+                                                        (const uint32_t*)ctx->sc_haff.p, (const uint8_t*)ctx->sc_hflag.p,
+                                                        (const uint32_t*)ctx->sc_saff.p, (const uint8_t*)ctx->sc_sflag.p, n_agg,
+                                                        (uint32_t*)ctx->sc_f.p);
+    CKL(ctx);
+    k_final_verdict<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_f.p, (const uint8_t*)ctx->sc_pkst.p,
+                                                        (const uint8_t*)ctx->sc_sflag.p, n_agg, d_ok);
+    CKL(ctx);
+    return B2_OK;
+}
+
+int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
+                                 const uint8_t* d_msg32, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok_out, void* stream) {
+    REQUIRE(ctx && d_members && d_off && d_bits && d_msg32 && d_sig96 && d_ok_out && n_agg > 0 && bits_stride > 0, "fast_aggregate_verify_dev: bad arguments");
+    REQUIRE(ctx->n_val > 0, "fast_aggregate_verify: registry not loaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = verify_tail(ctx, d_msg32, d_sig96, n_agg, d_ok_out, s, false))) return rc;
+    if ((rc = g1_aggregate_dev(ctx, d_members, d_off, d_bits, bits_stride, n_agg, s))) return rc;
+    return verify_join(ctx, n_agg, d_ok_out, s);
+}
+
+int b2_fast_aggregate_verify(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
+                             const uint8_t* msg32, const uint8_t* sig96, uint32_t n_agg, uint8_t* ok_out) {
+    REQUIRE(ctx && members && off && bits && msg32 && sig96 && ok_out && n_agg > 0 && bits_stride > 0, "fast_aggregate_verify: bad arguments");
+    REQUIRE(ctx->n_val > 0, "fast_aggregate_verify: registry not loaded");
+    int rc;
+    if ((rc = check_batch(ctx, members, off, bits_stride, n_agg, ctx->n_val))) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    if ((rc = upload_batch(ctx, members, off, bits, bits_stride, n_agg, s))) return rc;
+    if ((rc = ensure(ctx, ctx->in_d, (size_t)n_agg * 96)) || (rc = ensure(ctx, ctx->in_e, (size_t)n_agg * 32)) || (rc = ensure(ctx, ctx->out_a, n_agg)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->in_d.p, sig96, (size_t)n_agg * 96, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_e.p, msg32, (size_t)n_agg * 32, cudaMemcpyHostToDevice, s));
+    if ((rc = b2_fast_aggregate_verify_dev(ctx, (const uint32_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, (const uint8_t*)ctx->in_c.p, bits_stride,
+                                           (const uint8_t*)ctx->in_e.p, (const uint8_t*)ctx->in_d.p, n_agg, (uint8_t*)ctx->out_a.p, s)))
+        return rc;
+    std::vector<uint8_t> tok(n_agg);
+    CK(cudaMemcpyAsync(tok.data(), ctx->out_a.p, n_agg, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(ok_out, tok.data(), n_agg);
+    return B2_OK;
+}
+
+int b2_fast_aggregate_verify_pks(b2_ctx* ctx, const uint8_t* pk48, const uint32_t* pk_off, const uint8_t* msg32, const uint8_t* sig96,
+                                 uint32_t n_agg, uint8_t* ok_out) {
+    REQUIRE(ctx && pk_off && msg32 && sig96 && ok_out && n_agg > 0, "fast_aggregate_verify_pks: bad arguments");
+    REQUIRE(pk_off[0] == 0, "pk_off[0] must be 0");
+    for (uint32_t a = 0; a < n_agg; a++) REQUIRE(pk_off[a + 1] >= pk_off[a], "pk_off must be non-decreasing");
+    const uint64_t n_pk = pk_off[n_agg];
+    REQUIRE(n_pk == 0 || pk48, "null pubkeys");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_a, n_pk * 48 + 16)) || (rc = ensure(ctx, ctx->in_b, (size_t)(n_agg + 1) * 4)) ||
+        (rc = ensure(ctx, ctx->in_d, (size_t)n_agg * 96)) || (rc = ensure(ctx, ctx->in_e, (size_t)n_agg * 32)) || (rc = ensure(ctx, ctx->out_a, n_agg)) ||
+        (rc = ensure(ctx, ctx->sc_rec, n_pk * 96 + 16)) || (rc = ensure(ctx, ctx->sc_val, n_pk + 16)) ||
+        (rc = ensure(ctx, ctx->sc_pkjac, (size_t)n_agg * 144)) || (rc = ensure(ctx, ctx->sc_pkst, n_agg)))
+        return rc;
+    if (n_pk) CK(cudaMemcpyAsync(ctx->in_a.p, pk48, n_pk * 48, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_b.p, pk_off, (size_t)(n_agg + 1) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_d.p, sig96, (size_t)n_agg * 96, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_e.p, msg32, (size_t)n_agg * 32, cudaMemcpyHostToDevice, s));
+    if ((rc = verify_tail(ctx, (const uint8_t*)ctx->in_e.p, (const uint8_t*)ctx->in_d.p, n_agg, (uint8_t*)ctx->out_a.p, s, false))) return rc;
+    if (n_pk) {
+        k_g1_decompress_validate<<<blocks_for(n_pk, 128), 128, 0, s>>>((const uint8_t*)ctx->in_a.p, n_pk, (uint32_t*)ctx->sc_rec.p, (uint8_t*)ctx->sc_val.p);
+        CKL(ctx);
+    }
+    k_g1_segment_sum<<<n_agg, 128, 0, s>>>((const uint32_t*)ctx->sc_rec.p, (const uint8_t*)ctx->sc_val.p, (const uint32_t*)ctx->in_b.p, n_agg,
+                                           (uint32_t*)ctx->sc_pkjac.p, (uint8_t*)ctx->sc_pkst.p);
+    CKL(ctx);
+    if ((rc = verify_join(ctx, n_agg, (uint8_t*)ctx->out_a.p, s))) return rc;
+    std::vector<uint8_t> tok(n_agg);
+    CK(cudaMemcpyAsync(tok.data(), ctx->out_a.p, n_agg, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(ok_out, tok.data(), n_agg);
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ SkToPk / Sign / hash_to_g2
+int b2_sk_to_pk(b2_ctx* ctx, const uint32_t* sk8, uint64_t n, uint8_t* pk48_out) {
+    REQUIRE(ctx && sk8 && pk48_out && n > 0, "sk_to_pk: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_f, n * 32)) || (rc = ensure(ctx, ctx->out_a, n * 48))) return rc;
+    CK(cudaMemcpyAsync(ctx->in_f.p, sk8, n * 32, cudaMemcpyHostToDevice, s));
+    k_sk_to_pk<<<blocks_for(n, 64), 64, 0, s>>>((const uint32_t*)ctx->in_f.p, n, (uint8_t*)ctx->out_a.p);
+    CKL(ctx);
+    CK(cudaMemcpyAsync(pk48_out, ctx->out_a.p, n * 48, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
+int b2_hash_to_g2(b2_ctx* ctx, const uint8_t* msg32, uint32_t n_msg, uint8_t* out96) {
+    REQUIRE(ctx && msg32 && out96 && n_msg > 0, "hash_to_g2: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_e, (size_t)n_msg * 32)) || (rc = ensure(ctx, ctx->sc_haff, (size_t)n_msg * 192)) ||
+        (rc = ensure(ctx, ctx->sc_hflag, n_msg)) || (rc = ensure(ctx, ctx->out_a, (size_t)n_msg * 96)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->in_e.p, msg32, (size_t)n_msg * 32, cudaMemcpyHostToDevice, s));
+    k_hash_to_g2<<<blocks_for(n_msg, 32), 32, 0, s>>>((const uint8_t*)ctx->in_e.p, n_msg, (uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->sc_hflag.p);
+    CKL(ctx);
+    k_g2_compress_aff<<<blocks_for(n_msg, 64), 64, 0, s>>>((const uint32_t*)ctx->sc_haff.p, (const uint8_t*)ctx->sc_hflag.p, n_msg, (uint8_t*)ctx->out_a.p);
+    CKL(ctx);
+    CK(cudaMemcpyAsync(out96, ctx->out_a.p, (size_t)n_msg * 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
+int b2_sign(b2_ctx* ctx, const uint32_t* sk8, const uint32_t* msg_idx, uint64_t n, const uint8_t* msg32, uint32_t n_msg, uint8_t* sig96_out) {
+    REQUIRE(ctx && sk8 && msg_idx && msg32 && sig96_out && n > 0 && n_msg > 0, "sign: bad arguments");
+    for (uint64_t i = 0; i < n; i++) REQUIRE(msg_idx[i] < n_msg, "sign: msg_idx out of range");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_f, n * 32)) || (rc = ensure(ctx, ctx->in_g, n * 4)) || (rc = ensure(ctx, ctx->in_e, (size_t)n_msg * 32)) ||
+        (rc = ensure(ctx, ctx->sc_haff, (size_t)n_msg * 192)) || (rc = ensure(ctx, ctx->sc_hflag, n_msg)) || (rc = ensure(ctx, ctx->out_a, n * 96)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->in_f.p, sk8, n * 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_g.p, msg_idx, n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_e.p, msg32, (size_t)n_msg * 32, cudaMemcpyHostToDevice, s));
+    k_hash_to_g2<<<blocks_for(n_msg, 32), 32, 0, s>>>((const uint8_t*)ctx->in_e.p, n_msg, (uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->sc_hflag.p);
+    CKL(ctx);
+    k_sign<<<blocks_for(n, 64), 64, 0, s>>>((const uint32_t*)ctx->in_f.p, (const uint32_t*)ctx->in_g.p, n, (const uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->out_a.p);
+    CKL(ctx);
+    CK(cudaMemcpyAsync(sig96_out, ctx->out_a.p, n * 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ latest messages
+int b2_latest_messages_reset(b2_ctx* ctx) {
+    REQUIRE(ctx && ctx->n_val > 0, "latest_messages_reset: registry not loaded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_lmd_key, 0, ctx->n_val * 8, ctx->s_main));
+    CK(cudaMemsetAsync(ctx->d_lmd_block, 0, ctx->n_val * 4, ctx->s_main));
+    CK(cudaMemsetAsync(ctx->d_equiv, 0, ctx->n_val, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    return B2_OK;
+}
+
+int b2_latest_messages_load(b2_ctx* ctx, const uint64_t* epoch, const uint32_t* block_idx, const uint8_t* has_msg, const uint8_t* equivocating,
+                            uint64_t n) {
+    REQUIRE(ctx && epoch && block_idx && has_msg && equivocating && n == ctx->n_val && n > 0, "latest_messages_load: bad arguments / registry size");
+    std::vector<unsigned long long> key(n);
+    for (uint64_t v = 0; v < n; v++) {
+        REQUIRE(!has_msg[v] || epoch[v] < 0xffffffffull, "latest_messages_load: epoch does not fit 32 bits");
+        key[v] = has_msg[v] ? ((epoch[v] << 32) | 0xffffffffull) : 0ull;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpyAsync(ctx->d_lmd_key, key.data(), n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_lmd_block, block_idx, n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_equiv, equivocating, n, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
+int b2_latest_messages_read(b2_ctx* ctx, uint64_t* epoch, uint32_t* block_idx, uint8_t* has_msg, uint64_t n) {
+    REQUIRE(ctx && epoch && block_idx && has_msg && n == ctx->n_val && n > 0, "latest_messages_read: bad arguments / registry size");
+    std::vector<unsigned long long> key(n);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpyAsync(key.data(), ctx->d_lmd_key, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(block_idx, ctx->d_lmd_block, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint64_t v = 0; v < n; v++) {
+        has_msg[v] = key[v] != 0;
+        epoch[v] = key[v] >> 32;
+        if (!has_msg[v]) block_idx[v] = 0;
+    }
+    return B2_OK;
+}
+
+int b2_latest_messages_update_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
+                                  const uint64_t* d_target_epoch, const uint32_t* d_block_idx, const uint8_t* d_accept, uint32_t n_agg, void* stream) {
+    REQUIRE(ctx && d_members && d_off && d_bits && d_target_epoch && d_block_idx && n_agg > 0 && bits_stride > 0, "latest_messages_update_dev: bad arguments");
+    REQUIRE(ctx->n_val > 0, "latest_messages_update: registry not loaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    k_lmd_phase1<<<n_agg, 128, 0, s>>>(d_members, d_off, d_bits, bits_stride, d_target_epoch, d_accept, ctx->d_equiv, n_agg, ctx->d_lmd_key);
+    CKL(ctx);
+    k_lmd_phase2<<<n_agg, 128, 0, s>>>(d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_accept, ctx->d_equiv, n_agg,
+                                       ctx->d_lmd_key, ctx->d_lmd_block);
+    CKL(ctx);
+    return B2_OK;
+}
+
+int b2_latest_messages_update(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
+                              const uint64_t* target_epoch, const uint32_t* block_idx, const uint8_t* accept, uint32_t n_agg) {
+    REQUIRE(ctx && members && off && bits && target_epoch && block_idx && n_agg > 0 && bits_stride > 0, "latest_messages_update: bad arguments");
+    REQUIRE(ctx->n_val > 0, "latest_messages_update: registry not loaded");
+    int rc;
+    if ((rc = check_batch(ctx, members, off, bits_stride, n_agg, ctx->n_val))) return rc;
+    for (uint32_t a = 0; a < n_agg; a++) REQUIRE(target_epoch[a] < 0xffffffffull, "latest_messages_update: epoch does not fit 32 bits");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    if ((rc = upload_batch(ctx, members, off, bits, bits_stride, n_agg, s))) return rc;
+    if ((rc = ensure(ctx, ctx->in_d, (size_t)n_agg * 8)) || (rc = ensure(ctx, ctx->in_e, (size_t)n_agg * 4)) || (rc = ensure(ctx, ctx->in_f, n_agg)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->in_d.p, target_epoch, (size_t)n_agg * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_e.p, block_idx, (size_t)n_agg * 4, cudaMemcpyHostToDevice, s));
+    if (accept) CK(cudaMemcpyAsync(ctx->in_f.p, accept, n_agg, cudaMemcpyHostToDevice, s));
+    if ((rc = b2_latest_messages_update_dev(ctx, (const uint32_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, (const uint8_t*)ctx->in_c.p, bits_stride,
+                                            (const uint64_t*)ctx->in_d.p, (const uint32_t*)ctx->in_e.p, accept ? (const uint8_t*)ctx->in_f.p : nullptr,
+                                            n_agg, s)))
+        return rc;
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ block tree
+int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, const uint8_t* root32, const uint8_t* leaf_viable, uint32_t n) {
+    REQUIRE(ctx && parent && slot && root32 && leaf_viable && n > 0, "tree_load: bad arguments");
+    for (uint32_t b = 1; b < n; b++) REQUIRE(parent[b] < b, "tree_load: blocks must be in topological order (parent[b] < b)");
+    // children in CSR form
+    std::vector<uint32_t> child_off(n + 1, 0), child_idx(n > 1 ? n - 1 : 0), fill(n, 0);
+    for (uint32_t b = 1; b < n; b++) child_off[parent[b] + 1]++;
+    for (uint32_t b = 0; b < n; b++) child_off[b + 1] += child_off[b];
+    for (uint32_t b = 1; b < n; b++) child_idx[child_off[parent[b]] + fill[parent[b]]++] = b;
+    // DFS pre-order numbering and subtree sizes
+    std::vector<uint32_t> pre(n), size(n, 1), stack;
+    stack.reserve(n);
+    stack.push_back(0);
+    uint32_t counter = 0;
+    while (!stack.empty()) {
+        uint32_t b = stack.back();
+        stack.pop_back();
+        pre[b] = counter++;
+        for (uint32_t k = child_off[b + 1]; k > child_off[b]; k--) stack.push_back(child_idx[k - 1]);
+    }
+    for (uint32_t b = n - 1; b >= 1; b--) size[parent[b]] += size[b];
+    // get_filtered_block_tree: keep a block iff a viable leaf lies below it
+    std::vector<uint8_t> keep(n, 0);
+    for (uint32_t b = 0; b < n; b++)
+        if (child_off[b + 1] == child_off[b]) keep[b] = leaf_viable[b] ? 1 : 0;
+    for (uint32_t b = n - 1; b >= 1; b--)
+        if (keep[b]) keep[parent[b]] = 1;
+    // lexicographic rank of the roots (the tie-break of get_head compares 32-byte roots)
+    std::vector<uint32_t> order(n), rank(n);
+    for (uint32_t b = 0; b < n; b++) order[b] = b;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        int c = memcmp(root32 + 32ull * x, root32 + 32ull * y, 32);
+        return c != 0 ? c < 0 : x < y;
+    });
+    for (uint32_t i = 0; i < n; i++) rank[order[i]] = i;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_pre, n)) || (rc = dev_alloc(ctx, &ctx->d_size, n)) || (rc = dev_alloc(ctx, &ctx->d_child_off, (size_t)n + 1)) ||
+        (rc = dev_alloc(ctx, &ctx->d_child_idx, n)) || (rc = dev_alloc(ctx, &ctx->d_rank, n)) || (rc = dev_alloc(ctx, &ctx->d_next, n)) ||
+        (rc = dev_alloc(ctx, &ctx->d_keep, n)) || (rc = dev_alloc(ctx, &ctx->d_votes, n)) || (rc = dev_alloc(ctx, &ctx->d_prefix, (size_t)n + 1)) ||
+        (rc = dev_alloc(ctx, &ctx->d_weight, n)) || (rc = dev_alloc(ctx, &ctx->d_head, 1)))
+        return rc;
+    cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpyAsync(ctx->d_pre, pre.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_size, size.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_child_off, child_off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (n > 1) CK(cudaMemcpyAsync(ctx->d_child_idx, child_idx.data(), (size_t)(n - 1) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_rank, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_keep, keep.data(), n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->d_votes, 0, (size_t)n * 8, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->n_blocks = n;
+    return B2_OK;
+}
+
+int b2_vote_weights_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, void* stream) {
+    REQUIRE(ctx && d_votes_preorder, "vote_weights_dev: bad arguments");
+    REQUIRE(ctx->n_val > 0 && ctx->n_blocks > 0, "vote_weights: registry or tree not loaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    k_ghost_votes<<<blocks_for(ctx->n_val, 256), 256, 0, s>>>(ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff,
+                                                              ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder);
+    CKL(ctx);
+    return B2_OK;
+}
+
+int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
+                           uint64_t* d_weight_out, uint32_t* d_head_idx_out, void* stream) {
+    REQUIRE(ctx && d_votes_preorder && d_head_idx_out, "head_from_votes_dev: bad arguments");
+    REQUIRE(ctx->n_blocks > 0, "head_from_votes: tree not loaded");
+    REQUIRE(justified_idx < ctx->n_blocks && boost_idx < (int32_t)ctx->n_blocks, "head_from_votes: block index out of range");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    ghost_tree_args A;
+    A.n = ctx->n_blocks;
+    A.pre = ctx->d_pre;
+    A.size = ctx->d_size;
+    A.child_off = ctx->d_child_off;
+    A.child_idx = ctx->d_child_idx;
+    A.rank = ctx->d_rank;
+    A.keep = ctx->d_keep;
+    A.votes = (unsigned long long*)d_votes_preorder;
+    A.prefix = ctx->d_prefix;
+    A.next = ctx->d_next;
+    A.weight_out = (unsigned long long*)d_weight_out;
+    A.head_out = d_head_idx_out;
+    A.justified = justified_idx;
+    A.boost_idx = boost_idx;
+    A.boost_score = boost_score;
+    size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 4;
+    A.use_smem = smem <= 200 * 1024;
+    k_ghost_tree<<<1, 1024, A.use_smem ? smem : 0, s>>>(A);
+    CKL(ctx);
+    return B2_OK;
+}
+
+int b2_get_weights(b2_ctx* ctx, int32_t boost_idx, uint64_t boost_score, uint64_t* weight_out) {
+    REQUIRE(ctx && weight_out, "get_weights: bad arguments");
+    REQUIRE(ctx->n_val > 0 && ctx->n_blocks > 0, "get_weights: registry or tree not loaded");
+    int rc;
+    cudaStream_t s = ctx->s_main;
+    if ((rc = b2_vote_weights_dev(ctx, (uint64_t*)ctx->d_votes, s))) return rc;
+    if ((rc = b2_head_from_votes_dev(ctx, (uint64_t*)ctx->d_votes, 0, boost_idx, boost_score, (uint64_t*)ctx->d_weight, ctx->d_head, s))) return rc;
+    CK(cudaMemcpyAsync(weight_out, ctx->d_weight, (size_t)ctx->n_blocks * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
+int b2_get_head(b2_ctx* ctx, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score, uint32_t* head_idx_out) {
+    REQUIRE(ctx && head_idx_out, "get_head: bad arguments");
+    REQUIRE(ctx->n_val > 0 && ctx->n_blocks > 0, "get_head: registry or tree not loaded");
+    int rc;
+    cudaStream_t s = ctx->s_main;
+    if ((rc = b2_vote_weights_dev(ctx, (uint64_t*)ctx->d_votes, s))) return rc;
+    if ((rc = b2_head_from_votes_dev(ctx, (uint64_t*)ctx->d_votes, justified_idx, boost_idx, boost_score, nullptr, ctx->d_head, s))) return rc;
+    uint32_t h = 0;
+    CK(cudaMemcpyAsync(&h, ctx->d_head, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *head_idx_out = h;
+    return B2_OK;
+}
+
+}  // extern "C"

@@ -82,7 +82,7 @@ template <class F> HD bool aff_on_curve(const aff<F>& a) {
 }
 
 // dbl-2009-l (a = 0): 2M + 5S.  Z = 0 stays Z = 0.
-template <class F> HD jac<F> pt_dbl(const jac<F>& p) {
+template <class F> HDN jac<F> pt_dbl(const jac<F>& p) {
     F A = f_sqr(p.x);
     F B = f_sqr(p.y);
     F C = f_sqr(B);
@@ -98,7 +98,7 @@ template <class F> HD jac<F> pt_dbl(const jac<F>& p) {
 }
 
 // madd-2007-bl: Jacobian + affine, 7M + 4S, all exceptional cases handled (rare branches)
-template <class F> HD jac<F> pt_add_mixed(const jac<F>& p, const aff<F>& q) {
+template <class F> HDN jac<F> pt_add_mixed(const jac<F>& p, const aff<F>& q) {
     if (pt_is_inf(p)) return pt_from_affine(q);
     F Z1Z1 = f_sqr(p.z);
     F U2 = f_mul(q.x, Z1Z1);
@@ -122,7 +122,7 @@ template <class F> HD jac<F> pt_add_mixed(const jac<F>& p, const aff<F>& q) {
 }
 
 // add-2007-bl: Jacobian + Jacobian, 11M + 5S
-template <class F> HD jac<F> pt_add(const jac<F>& p, const jac<F>& q) {
+template <class F> HDN jac<F> pt_add(const jac<F>& p, const jac<F>& q) {
     if (pt_is_inf(p)) return q;
     if (pt_is_inf(q)) return p;
     F Z1Z1 = f_sqr(p.z);
@@ -148,7 +148,7 @@ template <class F> HD jac<F> pt_add(const jac<F>& p, const jac<F>& q) {
     return r;
 }
 
-template <class F> HD bool pt_eq(const jac<F>& p, const jac<F>& q) {
+template <class F> HDN bool pt_eq(const jac<F>& p, const jac<F>& q) {
     bool pi = pt_is_inf(p), qi = pt_is_inf(q);
     if (pi || qi) return pi && qi;
     F Z1Z1 = f_sqr(p.z), Z2Z2 = f_sqr(q.z);
@@ -157,7 +157,7 @@ template <class F> HD bool pt_eq(const jac<F>& p, const jac<F>& q) {
 }
 
 // -> affine; returns false for infinity (out untouched)
-template <class F> HD bool pt_to_affine(const jac<F>& p, aff<F>& out) {
+template <class F> HDN bool pt_to_affine(const jac<F>& p, aff<F>& out) {
     if (pt_is_inf(p)) return false;
     F zi = f_inv(p.z);
     F zi2 = f_sqr(zi);
@@ -167,7 +167,7 @@ template <class F> HD bool pt_to_affine(const jac<F>& p, aff<F>& out) {
 }
 
 // [k]P for a scalar that is the same in every thread (loop-uniform branches): 64-bit k
-template <class F> HD jac<F> pt_mul_u64(const jac<F>& p, uint64_t k) {
+template <class F> HDN jac<F> pt_mul_u64(const jac<F>& p, uint64_t k) {
     jac<F> r = pt_inf<F>();
     bool started = false;
 #pragma unroll 1
@@ -181,7 +181,7 @@ template <class F> HD jac<F> pt_mul_u64(const jac<F>& p, uint64_t k) {
     return r;
 }
 // [k]P, k = `nlimbs` 32-bit limbs in the constant table (uniform)
-template <class F> HD jac<F> pt_mul_const(const jac<F>& p, int off, int nlimbs) {
+template <class F> HDN jac<F> pt_mul_const(const jac<F>& p, int off, int nlimbs) {
     const uint32_t* e = const_table() + off;
     jac<F> r = pt_inf<F>();
     bool started = false;
@@ -196,7 +196,7 @@ template <class F> HD jac<F> pt_mul_const(const jac<F>& p, int off, int nlimbs) 
     return r;
 }
 // [k]P for a per-thread scalar (8 x 32-bit limbs, little endian): branch-free double-and-always-add
-template <class F> HD jac<F> pt_mul_var(const jac<F>& p, const uint32_t* k) {
+template <class F> HDN jac<F> pt_mul_var(const jac<F>& p, const uint32_t* k) {
     jac<F> r = pt_inf<F>();
 #pragma unroll 1
     for (int i = 255; i >= 0; i--) {
@@ -211,7 +211,7 @@ template <class F> HD jac<F> pt_mul_var(const jac<F>& p, const uint32_t* k) {
 enum DecodeStatus : int { DEC_OK = 0, DEC_INF = 1, DEC_BAD = 2 };
 
 // 48 bytes -> affine G1 point (Montgomery coordinates).  On-curve is implied; subgroup NOT checked.
-HD int g1_decompress(const uint8_t* in, g1_aff& out) {
+HDN int g1_decompress(const uint8_t* in, g1_aff& out) {
     uint8_t b0 = in[0];
     if (!(b0 & 0x80)) return DEC_BAD;
     fp xc = fp_from_be48(in);
@@ -230,7 +230,7 @@ HD int g1_decompress(const uint8_t* in, g1_aff& out) {
     out.y = y;
     return DEC_OK;
 }
-HD void g1_compress_affine(const g1_aff& a, bool inf, uint8_t* out) {
+HDN void g1_compress_affine(const g1_aff& a, bool inf, uint8_t* out) {
     if (inf) {
 #pragma unroll 1
         for (int i = 0; i < 48; i++) out[i] = 0;
@@ -249,7 +249,7 @@ HD void g1_compress(const g1_jac& p, uint8_t* out) {
 }
 
 // 96 bytes (x.c1 || x.c0) -> affine G2 point.  On-curve implied; subgroup NOT checked.
-HD int g2_decompress(const uint8_t* in, g2_aff& out) {
+HDN int g2_decompress(const uint8_t* in, g2_aff& out) {
     uint8_t b0 = in[0];
     if (!(b0 & 0x80)) return DEC_BAD;
     fp x1c = fp_from_be48(in);
@@ -270,7 +270,7 @@ HD int g2_decompress(const uint8_t* in, g2_aff& out) {
     out.y = y;
     return DEC_OK;
 }
-HD void g2_compress_affine(const g2_aff& a, bool inf, uint8_t* out) {
+HDN void g2_compress_affine(const g2_aff& a, bool inf, uint8_t* out) {
     if (inf) {
 #pragma unroll 1
         for (int i = 0; i < 96; i++) out[i] = 0;
@@ -311,7 +311,7 @@ HD g2_jac g2_psi2(const g2_jac& p) {
 // Scott 2021 ("A note on group membership tests for G1, G2 and GT on BLS pairing-friendly curves"):
 // P in G2  <=>  psi(P) == [x]P.  x = -|x|.  Equivalent to the oracle's [r]P == O (tests/test_hostsim.py
 // checks both directions on subgroup and non-subgroup points).
-HD bool g2_in_subgroup(const g2_jac& p) {
+HDN bool g2_in_subgroup(const g2_jac& p) {
     if (pt_is_inf(p)) return true;
     g2_jac xp = pt_neg(pt_mul_u64(p, B2_X_ABS));
     return pt_eq(g2_psi(p), xp);

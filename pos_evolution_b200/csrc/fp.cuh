@@ -175,7 +175,7 @@ HD fp fp_mul8(const fp& a) { return fp_dbl(fp_mul4(a)); }
 
 // a^e for a 384-bit exponent stored canonically in the constant table at `off` (uniform across
 // threads, so the bit tests do not diverge).  Fixed 4-bit window, 96 windows.
-HD fp fp_pow_const(const fp& a, int off) {
+HDN fp fp_pow_const(const fp& a, int off) {
     fp tbl[16];
     tbl[0] = fp_one();
     tbl[1] = a;

@@ -59,7 +59,7 @@ HD fp6 fp6_mul_v(const fp6& x) {
     return r;
 }
 // Karatsuba, 6 Fp2 multiplications
-HD fp6 fp6_mul(const fp6& x, const fp6& y) {
+HDN fp6 fp6_mul(const fp6& x, const fp6& y) {
     fp2 v0 = fp2_mul(x.a0, y.a0);
     fp2 v1 = fp2_mul(x.a1, y.a1);
     fp2 v2 = fp2_mul(x.a2, y.a2);
@@ -73,7 +73,7 @@ HD fp6 fp6_mul(const fp6& x, const fp6& y) {
     return r;
 }
 // Chung-Hasan SQR2: 2 mul + 3 sqr in Fp2
-HD fp6 fp6_sqr(const fp6& x) {
+HDN fp6 fp6_sqr(const fp6& x) {
     fp2 s0 = fp2_sqr(x.a0);
     fp2 s1 = fp2_dbl(fp2_mul(x.a0, x.a1));
     fp2 s2 = fp2_sqr(fp2_add(fp2_sub(x.a0, x.a1), x.a2));
@@ -86,7 +86,7 @@ HD fp6 fp6_sqr(const fp6& x) {
     return r;
 }
 // x * (b0 + b1 v): 5 Fp2 multiplications
-HD fp6 fp6_mul_by_01(const fp6& x, const fp2& b0, const fp2& b1) {
+HDN fp6 fp6_mul_by_01(const fp6& x, const fp2& b0, const fp2& b1) {
     fp2 v0 = fp2_mul(x.a0, b0);
     fp2 v1 = fp2_mul(x.a1, b1);
     fp2 t0 = fp2_mul(fp2_add(x.a1, x.a2), b1);                 // a1 b1 + a2 b1
@@ -99,14 +99,14 @@ HD fp6 fp6_mul_by_01(const fp6& x, const fp2& b0, const fp2& b1) {
     return r;
 }
 // x * (b1 v): 3 Fp2 multiplications
-HD fp6 fp6_mul_by_1(const fp6& x, const fp2& b1) {
+HDN fp6 fp6_mul_by_1(const fp6& x, const fp2& b1) {
     fp6 r;
     r.a0 = fp2_mul_xi(fp2_mul(x.a2, b1));
     r.a1 = fp2_mul(x.a0, b1);
     r.a2 = fp2_mul(x.a1, b1);
     return r;
 }
-HD fp6 fp6_inv(const fp6& x) {
+HDN fp6 fp6_inv(const fp6& x) {
     fp2 t0 = fp2_sub(fp2_sqr(x.a0), fp2_mul_xi(fp2_mul(x.a1, x.a2)));
     fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(x.a2)), fp2_mul(x.a0, x.a1));
     fp2 t2 = fp2_sub(fp2_sqr(x.a1), fp2_mul(x.a0, x.a2));
@@ -134,7 +134,7 @@ HD fp12 fp12_conj(const fp12& x) {
     r.b1 = fp6_neg(x.b1);
     return r;
 }
-HD fp12 fp12_mul(const fp12& x, const fp12& y) {
+HDN fp12 fp12_mul(const fp12& x, const fp12& y) {
     fp6 t0 = fp6_mul(x.b0, y.b0);
     fp6 t1 = fp6_mul(x.b1, y.b1);
     fp6 t2 = fp6_mul(fp6_add(x.b0, x.b1), fp6_add(y.b0, y.b1));
@@ -144,7 +144,7 @@ HD fp12 fp12_mul(const fp12& x, const fp12& y) {
     return r;
 }
 // complex squaring: 2 Fp6 multiplications
-HD fp12 fp12_sqr(const fp12& x) {
+HDN fp12 fp12_sqr(const fp12& x) {
     fp6 t = fp6_mul(x.b0, x.b1);
     fp6 s = fp6_mul(fp6_add(x.b0, x.b1), fp6_add(x.b0, fp6_mul_v(x.b1)));
     fp12 r;
@@ -153,7 +153,7 @@ HD fp12 fp12_sqr(const fp12& x) {
     return r;
 }
 // multiply by a sparse line value  (l0 + l1 v) + (l4 v) w   -- 13 Fp2 multiplications
-HD fp12 fp12_mul_by_014(const fp12& x, const fp2& l0, const fp2& l1, const fp2& l4) {
+HDN fp12 fp12_mul_by_014(const fp12& x, const fp2& l0, const fp2& l1, const fp2& l4) {
     fp6 t0 = fp6_mul_by_01(x.b0, l0, l1);
     fp6 t1 = fp6_mul_by_1(x.b1, l4);
     fp6 t2 = fp6_mul_by_01(fp6_add(x.b0, x.b1), l0, fp2_add(l1, l4));
@@ -162,7 +162,7 @@ HD fp12 fp12_mul_by_014(const fp12& x, const fp2& l0, const fp2& l1, const fp2& 
     r.b1 = fp6_sub(fp6_sub(t2, t0), t1);
     return r;
 }
-HD fp12 fp12_inv(const fp12& x) {
+HDN fp12 fp12_inv(const fp12& x) {
     fp6 d = fp6_sub(fp6_sqr(x.b0), fp6_mul_v(fp6_sqr(x.b1)));
     fp6 di = fp6_inv(d);
     fp12 r;
@@ -173,7 +173,7 @@ HD fp12 fp12_inv(const fp12& x) {
 
 // p-power Frobenius.  In the basis w^k (k = 0..5: a0, b1.a0, a1, b1.a1, a2, b1.a2 of the tower)
 // coefficient g_k maps to conj(g_k) * gamma^k, gamma = xi^((p-1)/6)  (constants C_FROB1_k).
-HD fp12 fp12_frob(const fp12& x) {
+HDN fp12 fp12_frob(const fp12& x) {
     fp12 r;
     r.b0.a0 = fp2_conj(x.b0.a0);
     r.b1.a0 = fp2_mul(fp2_conj(x.b1.a0), fp2_load_const(C_FROB1_1));
@@ -184,7 +184,7 @@ HD fp12 fp12_frob(const fp12& x) {
     return r;
 }
 // p^2-power Frobenius: g_k -> g_k * norm(gamma^k) (constants C_FROB2_k, in Fp)
-HD fp12 fp12_frob2(const fp12& x) {
+HDN fp12 fp12_frob2(const fp12& x) {
     fp12 r;
     r.b0.a0 = x.b0.a0;
     r.b1.a0 = fp2_mul_fp(x.b1.a0, fp_load_const(C_FROB2_1));
@@ -203,7 +203,7 @@ HD void fp4_sqr(const fp2& a, const fp2& b, fp2& c0, fp2& c1) {
     c0 = fp2_add(fp2_mul_xi(t1), t0);
     c1 = fp2_sub(fp2_sub(fp2_sqr(fp2_add(a, b)), t0), t1);
 }
-HD fp12 fp12_cyclotomic_sqr(const fp12& x) {
+HDN fp12 fp12_cyclotomic_sqr(const fp12& x) {
     fp2 z0 = x.b0.a0, z4 = x.b0.a1, z3 = x.b0.a2, z2 = x.b1.a0, z1 = x.b1.a1, z5 = x.b1.a2;
     fp2 t0, t1, t2, t3;
     fp4_sqr(z0, z1, t0, t1);

@@ -66,7 +66,7 @@ HD fp2 fp2_conj(const fp2& a) {
     return r;
 }
 // Karatsuba: 3 Fp multiplications
-HD fp2 fp2_mul(const fp2& a, const fp2& b) {
+HDN fp2 fp2_mul(const fp2& a, const fp2& b) {
     fp t0 = fp_mul(a.c0, b.c0);
     fp t1 = fp_mul(a.c1, b.c1);
     fp s = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
@@ -76,14 +76,14 @@ HD fp2 fp2_mul(const fp2& a, const fp2& b) {
     return r;
 }
 // (a0+a1)(a0-a1) + 2*a0*a1*i : 2 Fp multiplications
-HD fp2 fp2_sqr(const fp2& a) {
+HDN fp2 fp2_sqr(const fp2& a) {
     fp t = fp_mul(a.c0, a.c1);
     fp2 r;
     r.c0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
     r.c1 = fp_dbl(t);
     return r;
 }
-HD fp2 fp2_mul_fp(const fp2& a, const fp& k) {
+HDN fp2 fp2_mul_fp(const fp2& a, const fp& k) {
     fp2 r;
     r.c0 = fp_mul(a.c0, k);
     r.c1 = fp_mul(a.c1, k);
@@ -100,7 +100,7 @@ HD fp2 fp2_mul3(const fp2& a) { return fp2_add(fp2_dbl(a), a); }
 HD fp2 fp2_mul4(const fp2& a) { return fp2_dbl(fp2_dbl(a)); }
 HD fp2 fp2_mul8(const fp2& a) { return fp2_dbl(fp2_mul4(a)); }
 
-HD fp2 fp2_inv(const fp2& a) {
+HDN fp2 fp2_inv(const fp2& a) {
     fp n = fp_add(fp_sqr(a.c0), fp_sqr(a.c1));
     fp d = fp_inv(n);
     fp2 r;
@@ -114,7 +114,7 @@ HD fp2 fp2_inv(const fp2& a) {
 //   If x^2 == t:  root = x + (a1*d/2) i          (d = 1/x)
 //   else       :  root = (a1*d/2) - x i          (d^2 = -1/t, so (a1*d/2)^2 = (a0 - s)/2)
 // Returns false when `a` is not a square.  Any root; callers fix the sign.
-HD bool fp2_sqrt(const fp2& a, fp2& r) {
+HDN bool fp2_sqrt(const fp2& a, fp2& r) {
     if (fp_is_zero(a.c1)) {                      // a in Fp: always a square in Fp2
         fp x;
         bool qr = fp_sqrt(a.c0, x);              // x = a0^((p+1)/4); x^2 = -a0 when a0 is a non-residue

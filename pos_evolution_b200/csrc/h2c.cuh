@@ -29,7 +29,7 @@ HD uint32_t sha_k(int i) {
         0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
     return K[i];
 }
-HD void sha256_compress(uint32_t* h, const uint8_t* blk) {
+HDN void sha256_compress(uint32_t* h, const uint8_t* blk) {
     uint32_t w[64];
 #pragma unroll
     for (int i = 0; i < 16; i++)
@@ -90,7 +90,7 @@ HD void sha256_final(sha256_ctx& c, uint8_t* out) {
 }
 
 // expand_message_xmd(msg, DST, 256) -> 8 blocks of 32 bytes (RFC 9380 section 5.3.1)
-HD void expand_message_xmd_256(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len, uint8_t* out) {
+HDN void expand_message_xmd_256(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len, uint8_t* out) {
     uint8_t b0[32], bi[32], tmp[32];
     uint8_t dlen = (uint8_t)dst_len;
     sha256_ctx c;
@@ -134,7 +134,7 @@ HD fp fp_from_be64_reduce(const uint8_t* in) {
 }
 
 // hash_to_field with m = 2, count = 2 (RFC 9380 section 5.2)
-HD void hash_to_field_fp2x2(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len, fp2& u0, fp2& u1) {
+HDN void hash_to_field_fp2x2(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len, fp2& u0, fp2& u1) {
     uint8_t uniform[256];
     expand_message_xmd_256(msg, msg_len, dst, dst_len, uniform);
     u0.c0 = fp_from_be64_reduce(uniform);
@@ -145,7 +145,7 @@ HD void hash_to_field_fp2x2(const uint8_t* msg, uint32_t msg_len, const uint8_t*
 
 // ------------------------------------------------------------------------------------------ SSWU
 // Second half of the Fp2 square root: given s with s^2 = norm(a) and a.c1 != 0, one exponentiation.
-HD fp2 fp2_sqrt_given_norm_root(const fp2& a, const fp& s) {
+HDN fp2 fp2_sqrt_given_norm_root(const fp2& a, const fp& s) {
     fp half = fp_load_const(C_TWO_INV);
     fp t = fp_mul(fp_add(a.c0, s), half);
     fp d = fp_pow_pm3d4(t);
@@ -165,7 +165,7 @@ HD fp2 fp2_sqrt_given_norm_root(const fp2& a, const fp& s) {
 //       s^2 = -norm(gx1) and sqrt(norm(gx2)) = norm(Z) * norm(u)^3 * zeta * s with
 //       zeta = sqrt(-norm(Z)) -- no second norm exponentiation is needed;
 //   (3) the Fp2 root of whichever of gx1 / gx2 is the square.
-HD void sswu_map(const fp2& u, fp2& x_out, fp2& y_out) {
+HDN void sswu_map(const fp2& u, fp2& x_out, fp2& y_out) {
     const fp2 A = fp2_load_const(C_SSWU_A), B = fp2_load_const(C_SSWU_B), Z = fp2_load_const(C_SSWU_Z);
     fp2 u2 = fp2_sqr(u);
     fp2 zu2 = fp2_mul(Z, u2);
@@ -206,7 +206,7 @@ HD fp2 iso_horner(const fp2& x, int off, int ncoef, bool monic) {
     for (int i = ncoef - 2; i >= 0; i--) acc = fp2_add(fp2_mul(acc, x), fp2_load_const(off + 24 * i));
     return acc;
 }
-HD g2_jac iso3_map(const fp2& x, const fp2& y) {
+HDN g2_jac iso3_map(const fp2& x, const fp2& y) {
     fp2 xn = iso_horner(x, C_ISO_XNUM0, 4, false);
     fp2 xd = iso_horner(x, C_ISO_XDEN0, 2, true);
     fp2 yn = iso_horner(x, C_ISO_YNUM0, 4, false);
@@ -221,7 +221,7 @@ HD g2_jac iso3_map(const fp2& x, const fp2& y) {
 }
 
 // clear_cofactor_bls12381_g2 (RFC 9380 appendix G.3) == multiplication by h_eff
-HD g2_jac g2_clear_cofactor(const g2_jac& p) {
+HDN g2_jac g2_clear_cofactor(const g2_jac& p) {
     g2_jac t1 = pt_neg(pt_mul_u64(p, B2_X_ABS));          // c1 * P, c1 = x < 0
     g2_jac t2 = g2_psi(p);
     g2_jac t3 = g2_psi2(pt_dbl(p));
@@ -240,7 +240,7 @@ HD g2_jac map_to_curve_g2(const fp2& u) {
 }
 
 // hash_to_curve -> Jacobian point in G2
-HD g2_jac hash_to_g2(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len) {
+HDN g2_jac hash_to_g2(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len) {
     fp2 u0, u1;
     hash_to_field_fp2x2(msg, msg_len, dst, dst_len, u0, u1);
     g2_jac q = pt_add(map_to_curve_g2(u0), map_to_curve_g2(u1));

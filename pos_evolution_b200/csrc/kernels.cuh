@@ -1,0 +1,425 @@
+// kernels.cuh -- the __global__ kernels of libb200pos.so (sm_100a).  Per-thread bodies live in
+// cores.cuh (shared with the host-sim tests); this file adds thread mapping, warp-shuffle /
+// shared-memory tree reductions of partial EC points, and the fork-choice kernels K7-K9.
+// Kernel numbering follows SURVEY.md section 2.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "cores.cuh"
+
+namespace b2 {
+
+#define B2_FULL_MASK 0xffffffffu
+
+template <class T> __device__ __forceinline__ T shfl_down_pod(const T& v, int delta) {
+    constexpr int W = sizeof(T) / 4;
+    T r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < W; i++) d[i] = __shfl_down_sync(B2_FULL_MASK, s[i], delta);
+    return r;
+}
+
+// Sum of the per-thread partial points of a block; result valid in thread 0.  Warp level: shuffle
+// tree (5 rounds of Jacobian additions); across warps: shared memory.  `smem` holds blockDim/32 points.
+template <class F> __device__ __forceinline__ jac<F> block_sum_points(jac<F> acc, jac<F>* smem) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll 1
+    for (int delta = 16; delta >= 1; delta >>= 1) {
+        jac<F> other = shfl_down_pod(acc, delta);
+        if (lane < delta) acc = pt_add(acc, other);
+    }
+    if (lane == 0) smem[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (int w = 1; w < nwarp; w++) acc = pt_add(acc, smem[w]);
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------ registry
+__global__ void __launch_bounds__(128) k_registry_load(const uint8_t* __restrict__ pk48, uint64_t n, uint32_t* records, uint8_t* valid) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) core_registry_load(pk48, records, valid, i);
+}
+
+// ------------------------------------------------------------------------------------------ K2: G1 gather + aggregate
+// one block per aggregate; thread t takes members t, t+B, ...: bit test, index load, 96-byte record
+// gather (six 128-bit loads), mixed addition; then the block-level tree.
+__global__ void __launch_bounds__(128) k_g1_aggregate(const uint32_t* __restrict__ records, const uint8_t* __restrict__ valid,
+                                                       const uint32_t* __restrict__ members, const uint32_t* __restrict__ off,
+                                                       const uint8_t* __restrict__ bits, uint32_t bits_stride, uint32_t n_agg,
+                                                       uint32_t* out_jac, uint8_t* out_status) {
+    __shared__ g1_jac red[4];
+    const uint32_t a = blockIdx.x;
+    if (a >= n_agg) return;
+    const uint32_t size = off[a + 1] - off[a];
+    g1_jac acc = pt_inf<fp>();
+    uint32_t status = 0, cnt = 0;
+#pragma unroll 1
+    for (uint32_t j = threadIdx.x; j < size; j += blockDim.x)
+        core_g1_accumulate(records, valid, members, off, bits, bits_stride, a, j, acc, status, cnt);
+    acc = block_sum_points(acc, red);
+    status = __syncthreads_or((int)status);
+    cnt = __syncthreads_count(cnt != 0);
+    if (threadIdx.x == 0) core_g1_finish(acc, status, cnt, a, out_jac, out_status);
+}
+
+// Jacobian aggregated pubkeys -> compressed 48 bytes (only for the b2_g1_aggregate entry point)
+__global__ void __launch_bounds__(64) k_g1_compress(const uint32_t* __restrict__ jac_in, uint32_t n, uint8_t* out48) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g1_compress(load_g1_jac(jac_in + 36 * (uint64_t)i), out48 + 48 * (uint64_t)i);
+}
+
+// pyspec-literal form: decompress + KeyValidate explicit pubkeys, then sum per aggregate
+__global__ void __launch_bounds__(128) k_g1_decompress_validate(const uint8_t* __restrict__ pk48, uint64_t n, uint32_t* records, uint8_t* valid) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) core_registry_load(pk48, records, valid, i);
+}
+__global__ void __launch_bounds__(128) k_g1_segment_sum(const uint32_t* __restrict__ records, const uint8_t* __restrict__ valid,
+                                                         const uint32_t* __restrict__ off, uint32_t n_agg, uint32_t* out_jac, uint8_t* out_status) {
+    __shared__ g1_jac red[4];
+    const uint32_t a = blockIdx.x;
+    if (a >= n_agg) return;
+    g1_jac acc = pt_inf<fp>();
+    uint32_t status = 0, cnt = 0;
+#pragma unroll 1
+    for (uint32_t j = off[a] + threadIdx.x; j < off[a + 1]; j += blockDim.x) {
+        cnt++;
+        if (!valid[j]) {
+            status |= PK_INVALID_KEY;
+        } else {
+            acc = pt_add_mixed(acc, load_record(records, j));
+        }
+    }
+    acc = block_sum_points(acc, red);
+    status = __syncthreads_or((int)status);
+    cnt = __syncthreads_count(cnt != 0);
+    if (threadIdx.x == 0) core_g1_finish(acc, status, cnt, a, out_jac, out_status);
+}
+
+// ------------------------------------------------------------------------------------------ K3: bls.Aggregate
+// stage 1: one thread per signature: ZCash decode + Fp2 square root (two Fp exponentiations) -> affine point
+__global__ void __launch_bounds__(128) k_g2_decompress(const uint8_t* __restrict__ sig96, uint64_t n, uint32_t* aff_out, uint8_t* st_out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_aff s;
+    s.x = fp2_zero();
+    s.y = fp2_zero();
+    int st = g2_decompress(sig96 + 96 * i, s);
+    uint4* o = reinterpret_cast<uint4*>(aff_out + 48 * i);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    st_out[i] = (uint8_t)st;
+}
+// stage 2: one block per segment: mixed additions + tree, compress
+__global__ void __launch_bounds__(128) k_g2_segment_sum(const uint32_t* __restrict__ aff, const uint8_t* __restrict__ st,
+                                                         const uint32_t* __restrict__ seg_off, uint32_t n_seg, uint8_t* out96,
+                                                         int32_t* seg_status) {
+    __shared__ g2_jac red[4];
+    const uint32_t s = blockIdx.x;
+    if (s >= n_seg) return;
+    const uint32_t begin = seg_off[s], end = seg_off[s + 1];
+    g2_jac acc = pt_inf<fp2>();
+    uint32_t bad = 0;
+#pragma unroll 1
+    for (uint32_t j = begin + threadIdx.x; j < end; j += blockDim.x) {
+        uint8_t f = st[j];
+        if (f == DEC_BAD) {
+            bad = 1;
+        } else if (f == DEC_OK) {
+            g2_aff p;
+            const uint4* in = reinterpret_cast<const uint4*>(aff + 48 * (uint64_t)j);
+            uint32_t* w = reinterpret_cast<uint32_t*>(&p);
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                uint4 v = in[k];
+                w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+            }
+            acc = pt_add_mixed(acc, p);
+        }
+    }
+    acc = block_sum_points(acc, red);
+    bad = __syncthreads_or((int)bad);
+    if (threadIdx.x == 0) core_g2_agg_finish(acc, bad, end - begin, s, out96, seg_status);
+}
+
+// ------------------------------------------------------------------------------------------ K4-K6: verification pipeline
+__global__ void __launch_bounds__(32) k_hash_to_g2(const uint8_t* __restrict__ msg32, uint32_t n, uint32_t* h_aff, uint8_t* hflag) {
+    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    g2_aff h;
+    uint8_t f;
+    core_hash_msg(msg32, a, h, f);
+    uint32_t* o = h_aff + 48 * (uint64_t)a;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&h);
+#pragma unroll
+    for (int k = 0; k < 48; k++) o[k] = w[k];
+    hflag[a] = f;
+}
+__global__ void __launch_bounds__(32) k_sig_prepare(const uint8_t* __restrict__ sig96, uint32_t n, uint32_t* s_aff, uint8_t* sflag) {
+    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    g2_aff s;
+    uint8_t f;
+    core_sig_prepare(sig96, a, s, f);
+    uint32_t* o = s_aff + 48 * (uint64_t)a;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&s);
+#pragma unroll
+    for (int k = 0; k < 48; k++) o[k] = w[k];
+    sflag[a] = f;
+}
+__device__ __forceinline__ g2_aff load_g2_aff(const uint32_t* p) {
+    g2_aff r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < 48; k++) w[k] = p[k];
+    return r;
+}
+// thread 2a: miller(PK_agg[a], H(m_a));  thread 2a+1: miller(-g1, sig_a)
+__global__ void __launch_bounds__(32) k_miller(const uint32_t* __restrict__ pk_jac, const uint8_t* __restrict__ pk_status,
+                                                const uint32_t* __restrict__ h_aff, const uint8_t* __restrict__ hflag,
+                                                const uint32_t* __restrict__ s_aff, const uint8_t* __restrict__ sflag, uint32_t n_agg,
+                                                uint32_t* f_out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n_agg) return;
+    uint32_t a = t >> 1;
+    fp12 f;
+    if (t & 1) {
+        f = core_miller_sig(load_g2_aff(s_aff + 48 * (uint64_t)a), sflag[a]);
+    } else {
+        f = core_miller_pk(pk_jac, pk_status, a, load_g2_aff(h_aff + 48 * (uint64_t)a), hflag[a]);
+    }
+    uint32_t* o = f_out + 144 * (uint64_t)t;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&f);
+#pragma unroll 1
+    for (int k = 0; k < 144; k++) o[k] = w[k];
+}
+__global__ void __launch_bounds__(32) k_final_verdict(const uint32_t* __restrict__ f_in, const uint8_t* __restrict__ pk_status,
+                                                       const uint8_t* __restrict__ sflag, uint32_t n_agg, uint8_t* ok) {
+    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_agg) return;
+    fp12 f0, f1;
+    uint32_t* w0 = reinterpret_cast<uint32_t*>(&f0);
+    uint32_t* w1 = reinterpret_cast<uint32_t*>(&f1);
+    const uint32_t* p = f_in + 288 * (uint64_t)a;
+#pragma unroll 1
+    for (int k = 0; k < 144; k++) {
+        w0[k] = p[k];
+        w1[k] = p[144 + k];
+    }
+    ok[a] = core_final_verdict(f0, f1, pk_status[a], sflag[a]);
+}
+
+// ------------------------------------------------------------------------------------------ bls.SkToPk / bls.Sign (data generation, tests)
+__global__ void __launch_bounds__(64) k_sk_to_pk(const uint32_t* __restrict__ sk8, uint64_t n, uint8_t* pk48) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_jac g;
+    g.x = fp_load_const(C_G1X);
+    g.y = fp_load_const(C_G1Y);
+    g.z = fp_one();
+    uint32_t k[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = sk8[8 * i + j];
+    g1_compress(pt_mul_var(g, k), pk48 + 48 * i);
+}
+__global__ void __launch_bounds__(64) k_sign(const uint32_t* __restrict__ sk8, const uint32_t* __restrict__ msg_idx, uint64_t n,
+                                              const uint32_t* __restrict__ h_aff, uint8_t* sig96) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_jac h = pt_from_affine(load_g2_aff(h_aff + 48 * (uint64_t)msg_idx[i]));
+    uint32_t k[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = sk8[8 * i + j];
+    g2_compress(pt_mul_var(h, k), sig96 + 96 * i);
+}
+__global__ void __launch_bounds__(64) k_g2_compress_aff(const uint32_t* __restrict__ aff, const uint8_t* __restrict__ inf, uint32_t n, uint8_t* out96) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_compress_affine(load_g2_aff(aff + 48 * (uint64_t)i), inf[i] != 0, out96 + 96 * (uint64_t)i);
+}
+
+// ------------------------------------------------------------------------------------------ K7: update_latest_messages
+// Order-exact parallel form of /root/reference/pos-evolution.md:1435-1441.  Table entry = u64 key
+// (epoch << 32 | 0xffffffff - order); a stored message has order 0, attestation a of the batch has
+// order a+1, so atomicMax picks "highest epoch, earliest in list, stored wins ties" -- exactly the
+// sequential rule `i not in latest_messages or target.epoch > latest_messages[i].epoch`.
+__device__ __forceinline__ bool lmd_member(const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t stride, uint32_t a,
+                                           uint32_t j, uint32_t& v) {
+    if (!((bits[(uint64_t)a * stride + (j >> 3)] >> (j & 7)) & 1)) return false;
+    v = members[off[a] + j];
+    return true;
+}
+__global__ void __launch_bounds__(128) k_lmd_phase1(const uint32_t* __restrict__ members, const uint32_t* __restrict__ off,
+                                                     const uint8_t* __restrict__ bits, uint32_t stride, const uint64_t* __restrict__ target_epoch,
+                                                     const uint8_t* __restrict__ accept, const uint8_t* __restrict__ equiv, uint32_t n_agg,
+                                                     unsigned long long* lmd_key) {
+    uint32_t a = blockIdx.x;
+    if (a >= n_agg || (accept && !accept[a])) return;
+    unsigned long long key = ((unsigned long long)target_epoch[a] << 32) | (0xffffffffull - (a + 1));
+    uint32_t size = off[a + 1] - off[a], v;
+    for (uint32_t j = threadIdx.x; j < size; j += blockDim.x)
+        if (lmd_member(members, off, bits, stride, a, j, v) && !equiv[v]) atomicMax(&lmd_key[v], key);
+}
+__global__ void __launch_bounds__(128) k_lmd_phase2(const uint32_t* __restrict__ members, const uint32_t* __restrict__ off,
+                                                     const uint8_t* __restrict__ bits, uint32_t stride, const uint64_t* __restrict__ target_epoch,
+                                                     const uint32_t* __restrict__ block_idx, const uint8_t* __restrict__ accept,
+                                                     const uint8_t* __restrict__ equiv, uint32_t n_agg, unsigned long long* lmd_key,
+                                                     uint32_t* lmd_block) {
+    uint32_t a = blockIdx.x;
+    if (a >= n_agg || (accept && !accept[a])) return;
+    unsigned long long key = ((unsigned long long)target_epoch[a] << 32) | (0xffffffffull - (a + 1));
+    uint32_t size = off[a + 1] - off[a], v;
+    for (uint32_t j = threadIdx.x; j < size; j += blockDim.x)
+        if (lmd_member(members, off, bits, stride, a, j, v) && !equiv[v] && lmd_key[v] == key) {
+            lmd_block[v] = block_idx[a];
+            lmd_key[v] = key | 0xffffffffull;
+        }
+}
+
+// ------------------------------------------------------------------------------------------ K8: vote scatter
+// One thread per validator: coalesced reads of the latest-message table (u64 key + u32 block), the
+// effective-balance table (u64) and two byte masks; votes are combined inside the warp (lanes voting
+// for the same block elect a leader) and the leader issues one 64-bit atomic add into the pre-order
+// vote array, so that a head everybody agrees on does not serialise a million atomics on one address.
+__global__ void __launch_bounds__(256) k_ghost_votes(uint64_t n, const unsigned long long* __restrict__ lmd_key,
+                                                      const uint32_t* __restrict__ lmd_block, const uint8_t* __restrict__ equiv,
+                                                      const uint8_t* __restrict__ flags, const uint64_t* __restrict__ eff,
+                                                      const uint32_t* __restrict__ pre, uint32_t n_blocks, unsigned long long* votes) {
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool on = v < n;
+    uint32_t b = 0xffffffffu;
+    unsigned long long bal = 0;
+    if (on) {
+        on = lmd_key[v] != 0 && !equiv[v] && (flags[v] & 1);
+        if (on) {
+            uint32_t blk = lmd_block[v];
+            on = blk < n_blocks;
+            if (on) {
+                b = pre[blk];
+                bal = eff[v];
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    unsigned peers = __match_any_sync(B2_FULL_MASK, b);
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int l = 0; l < 32; l++) {
+        unsigned long long o = __shfl_sync(B2_FULL_MASK, bal, l);
+        if ((peers >> l) & 1u) sum += o;
+    }
+    if (on && lane == __ffs(peers) - 1) atomicAdd(&votes[b], sum);
+}
+
+// ------------------------------------------------------------------------------------------ K9: subtree weights + head
+// Single block.  Blocks were renumbered in DFS pre-order at b2_tree_load, so the subtree of b is the
+// contiguous range [pre[b], pre[b]+size[b]) and get_latest_attesting_balance(b) is a difference of two
+// prefix sums of the direct votes (+ proposer boost on one block).  The head walk of get_head
+// (argmax over children of (weight, root), repeated to a leaf) is done for all blocks at once:
+// best_child[], then pointer jumping (log2(depth) rounds) from the justified root.
+// Scratch arrays live in shared memory when they fit, else in global memory.
+struct ghost_tree_args {
+    uint32_t n;
+    const uint32_t* pre;        // block -> pre-order position
+    const uint32_t* size;       // subtree size
+    const uint32_t* child_off;  // CSR children (block indices)
+    const uint32_t* child_idx;
+    const uint32_t* rank;       // lexicographic rank of the 32-byte root
+    const uint8_t* keep;        // get_filtered_block_tree membership
+    unsigned long long* votes;  // in: direct votes in pre-order; zeroed on exit
+    unsigned long long* prefix; // scratch n+1 (global fallback)
+    uint32_t* next;             // scratch n   (global fallback)
+    unsigned long long* weight_out;  // optional, per block
+    uint32_t* head_out;
+    uint32_t justified;
+    int32_t boost_idx;
+    unsigned long long boost_score;
+    int use_smem;
+};
+__global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
+    extern __shared__ unsigned long long smem_u64[];
+    __shared__ unsigned long long warp_tot[32];
+    const uint32_t n = A.n, tid = threadIdx.x, T = blockDim.x;
+    unsigned long long* S = A.use_smem ? smem_u64 : A.prefix;
+    uint32_t* next = A.use_smem ? reinterpret_cast<uint32_t*>(smem_u64 + (n + 1)) : A.next;
+    if (tid == 0 && A.boost_idx >= 0) A.votes[A.pre[A.boost_idx]] += A.boost_score;
+    __syncthreads();
+    // exclusive prefix sum of votes[0..n) -> S[0..n]
+    const uint32_t per = (n + T - 1) / T;
+    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
+    unsigned long long local = 0;
+    for (uint32_t i = lo; i < hi; i++) local += A.votes[i];
+    unsigned long long incl = local;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(B2_FULL_MASK, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = (lane < (int)(T >> 5)) ? warp_tot[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long o = __shfl_up_sync(B2_FULL_MASK, wi, d);
+            if (lane >= d) wi += o;
+        }
+        warp_tot[lane] = wi - w;                 // exclusive offset of each warp
+    }
+    __syncthreads();
+    unsigned long long run = warp_tot[warp] + incl - local;
+    for (uint32_t i = lo; i < hi; i++) {
+        S[i] = run;
+        run += A.votes[i];
+        A.votes[i] = 0;                          // leave the accumulator clean for the next call
+    }
+    if (hi == n && lo < n) S[n] = run;
+    if (n == 0 && tid == 0) S[0] = 0;
+    __syncthreads();
+    // weights and best child
+    for (uint32_t b = tid; b < n; b += T) {
+        uint32_t p = A.pre[b];
+        if (A.weight_out) A.weight_out[b] = S[p + A.size[b]] - S[p];
+        uint32_t best = b;
+        unsigned long long bw = 0;
+        uint32_t br = 0;
+        bool have = false;
+        if (A.keep[b]) {
+            for (uint32_t k = A.child_off[b]; k < A.child_off[b + 1]; k++) {
+                uint32_t c = A.child_idx[k];
+                if (!A.keep[c]) continue;
+                uint32_t pc = A.pre[c];
+                unsigned long long w = S[pc + A.size[c]] - S[pc];
+                uint32_t r = A.rank[c];
+                if (!have || w > bw || (w == bw && r > br)) {
+                    have = true;
+                    best = c;
+                    bw = w;
+                    br = r;
+                }
+            }
+        }
+        next[b] = best;
+    }
+    __syncthreads();
+    // pointer jumping: after k rounds next[b] is at least 2^k steps down b's best path (or its leaf).
+    // Updated in place: a racing reader sees either the old or the new hop target of another block; both lie
+    // on the same best path, the hop distance still at least doubles per round, and the fix point is the leaf.
+    volatile uint32_t* vn = next;
+    for (uint32_t span = 1; span < n; span <<= 1) {
+        for (uint32_t b = tid; b < n; b += T) {
+            uint32_t t2 = vn[vn[b]];
+            vn[b] = t2;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *A.head_out = (A.justified < n) ? next[A.justified] : 0xffffffffu;
+}
+
+}  // namespace b2

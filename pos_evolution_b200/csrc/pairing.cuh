@@ -36,7 +36,7 @@ HD miller_p miller_p_from_jac(const g1_jac& p) {
 
 // tangent at T (Jacobian), then T <- 2T.   slope = 3X^2 / (2YZ); scaled by 2YZ^3 = Z3 * Z^2:
 //   c0 = 3X^3 - 2Y^2,  c1 = -3X^2 Z^2 * xP,  d1 = Z3 Z^2 * yP
-HD void miller_dbl_step(g2_jac& T, const miller_p& P, line_coeffs& l) {
+HDN void miller_dbl_step(g2_jac& T, const miller_p& P, line_coeffs& l) {
     fp2 A = fp2_sqr(T.x);
     fp2 B = fp2_sqr(T.y);
     fp2 C = fp2_sqr(B);
@@ -55,7 +55,7 @@ HD void miller_dbl_step(g2_jac& T, const miller_p& P, line_coeffs& l) {
 
 // chord through T (Jacobian) and Q (affine), then T <- T + Q.  slope = (S2 - Y)/(Z H); scaled by Z3 = 2ZH:
 //   c0 = r*xQ - yQ*Z3,  c1 = -r * xP,  d1 = Z3 * yP       (r = 2(S2 - Y))
-HD void miller_add_step(g2_jac& T, const g2_aff& Q, const miller_p& P, line_coeffs& l) {
+HDN void miller_add_step(g2_jac& T, const g2_aff& Q, const miller_p& P, line_coeffs& l) {
     fp2 Z1Z1 = fp2_sqr(T.z);
     fp2 U2 = fp2_mul(Q.x, Z1Z1);
     fp2 S2 = fp2_mul(fp2_mul(Q.y, T.z), Z1Z1);
@@ -76,7 +76,7 @@ HD void miller_add_step(g2_jac& T, const g2_aff& Q, const miller_p& P, line_coef
 }
 
 // f_{|x|,Q}(P), conjugated because x < 0.  Either argument at infinity -> 1 (as the oracle).
-HD fp12 miller_loop(const g1_jac& Pj, const g2_aff& Q, bool q_inf) {
+HDN fp12 miller_loop(const g1_jac& Pj, const g2_aff& Q, bool q_inf) {
     if (q_inf || pt_is_inf(Pj)) return fp12_one();
     miller_p P = miller_p_from_jac(Pj);
     g2_jac T = pt_from_affine(Q);
@@ -96,7 +96,7 @@ HD fp12 miller_loop(const g1_jac& Pj, const g2_aff& Q, bool q_inf) {
 }
 
 // a^|x| for a in the cyclotomic subgroup
-HD fp12 fp12_cyc_exp_x_abs(const fp12& a) {
+HDN fp12 fp12_cyc_exp_x_abs(const fp12& a) {
     fp12 r = a;
 #pragma unroll 1
     for (int i = 62; i >= 0; i--) {
@@ -110,7 +110,7 @@ HD fp12 fp12_cyc_exp_x(const fp12& a) { return fp12_conj(fp12_cyc_exp_x_abs(a));
 
 // f^(3*(p^12-1)/r): easy part (p^6-1)(p^2+1), hard part by the Hayashida-Hayasaka-Teruya chain
 //   3*Phi12(p)/r = (x-1)^2 (x+p) (x^2+p^2-1) + 3
-HD fp12 final_exponentiation(const fp12& f) {
+HDN fp12 final_exponentiation(const fp12& f) {
     fp12 t = fp12_mul(fp12_conj(f), fp12_inv(f));
     fp12 m = fp12_mul(fp12_frob2(t), t);
     fp12 a = fp12_mul(fp12_cyc_exp_x(m), fp12_conj(m));

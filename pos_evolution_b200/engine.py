@@ -1,0 +1,222 @@
+"""Array-level host API over the C ABI: one Engine = one b2_ctx = one GPU.
+
+Everything here takes/returns flat numpy arrays (host entry points) or torch CUDA tensors
+(`*_dev`, asynchronous on torch's current stream).  The pyspec-signature layer (bls.py, spec.py)
+and bench.py are built on it.  No CPU fallback: constructing an Engine without a B200 raises.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import B2Error
+
+
+def _c(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.b2_init(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise B2Error(rc, "b2_init(device=%d) failed -- a B200 (sm_100) GPU is required; there is no CPU fallback" % device)
+        self.h = h
+        self.device = device
+        self.n_validators = 0
+        self.n_blocks = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise B2Error(rc, self.lib.b2_last_error(self.h).decode())
+
+    def sync(self):
+        self._ck(self.lib.b2_sync(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.b2_launch_count(self.h))
+
+    # ------------------------------------------------------------------ registry
+    def registry_load(self, pubkeys48, effective_balance, flags=None):
+        """pubkeys48: uint8[N,48]; effective_balance: uint64[N]; flags: uint8[N] (bit0 active, bit1 slashed).
+        Returns uint8[N]: 1 where KeyValidate passed."""
+        pk = _c(pubkeys48, np.uint8).reshape(-1, 48)
+        n = pk.shape[0]
+        eff = _c(effective_balance, np.uint64)
+        fl = _c(flags if flags is not None else np.ones(n, dtype=np.uint8), np.uint8)
+        assert eff.shape == (n,) and fl.shape == (n,)
+        valid = np.zeros(n, dtype=np.uint8)
+        self._ck(self.lib.b2_registry_load(self.h, _p(pk), _p(eff), _p(fl), n, _p(valid)))
+        self.n_validators = n
+        return valid
+
+    def registry_update_balances(self, effective_balance, flags):
+        eff, fl = _c(effective_balance, np.uint64), _c(flags, np.uint8)
+        self._ck(self.lib.b2_registry_update_balances(self.h, _p(eff), _p(fl), eff.shape[0]))
+
+    # ------------------------------------------------------------------ BLS batches
+    @staticmethod
+    def _batch(members, off, bits):
+        members = _c(members, np.uint32)
+        off = _c(off, np.uint32)
+        bits = _c(bits, np.uint8)
+        n_agg = off.shape[0] - 1
+        assert bits.ndim == 2 and bits.shape[0] == n_agg
+        return members, off, bits, n_agg, bits.shape[1]
+
+    def g1_aggregate(self, members, off, bits):
+        members, off, bits, n_agg, stride = self._batch(members, off, bits)
+        out = np.zeros((n_agg, 48), dtype=np.uint8)
+        status = np.zeros(n_agg, dtype=np.uint8)
+        self._ck(self.lib.b2_g1_aggregate(self.h, _p(members), _p(off), _p(bits), stride, n_agg, _p(out), _p(status)))
+        return out, status
+
+    def aggregate(self, sigs96, seg_off):
+        sigs = _c(sigs96, np.uint8).reshape(-1, 96)
+        seg_off = _c(seg_off, np.uint32)
+        n_seg = seg_off.shape[0] - 1
+        assert int(seg_off[-1]) == sigs.shape[0]
+        out = np.zeros((n_seg, 96), dtype=np.uint8)
+        status = np.zeros(n_seg, dtype=np.int32)
+        self._ck(self.lib.b2_aggregate(self.h, _p(sigs), _p(seg_off), n_seg, _p(out), _p(status)))
+        return out, status
+
+    def fast_aggregate_verify(self, members, off, bits, msgs32, sigs96):
+        members, off, bits, n_agg, stride = self._batch(members, off, bits)
+        msgs = _c(msgs32, np.uint8).reshape(n_agg, 32)
+        sigs = _c(sigs96, np.uint8).reshape(n_agg, 96)
+        ok = np.zeros(n_agg, dtype=np.uint8)
+        self._ck(self.lib.b2_fast_aggregate_verify(self.h, _p(members), _p(off), _p(bits), stride, _p(msgs), _p(sigs), n_agg, _p(ok)))
+        return ok
+
+    def fast_aggregate_verify_pks(self, pks48, pk_off, msgs32, sigs96):
+        pk_off = _c(pk_off, np.uint32)
+        n_agg = pk_off.shape[0] - 1
+        pks = _c(pks48, np.uint8).reshape(-1, 48)
+        assert int(pk_off[-1]) == pks.shape[0]
+        msgs = _c(msgs32, np.uint8).reshape(n_agg, 32)
+        sigs = _c(sigs96, np.uint8).reshape(n_agg, 96)
+        ok = np.zeros(n_agg, dtype=np.uint8)
+        self._ck(self.lib.b2_fast_aggregate_verify_pks(self.h, _p(pks), _p(pk_off), _p(msgs), _p(sigs), n_agg, _p(ok)))
+        return ok
+
+    @staticmethod
+    def _sk_limbs(sks):
+        out = np.zeros((len(sks), 8), dtype=np.uint32)
+        for i, k in enumerate(sks):
+            k = int(k)
+            for j in range(8):
+                out[i, j] = (k >> (32 * j)) & 0xFFFFFFFF
+        return out
+
+    def sk_to_pk(self, sks):
+        sk8 = sks if isinstance(sks, np.ndarray) else self._sk_limbs(sks)
+        sk8 = _c(sk8, np.uint32).reshape(-1, 8)
+        out = np.zeros((sk8.shape[0], 48), dtype=np.uint8)
+        self._ck(self.lib.b2_sk_to_pk(self.h, _p(sk8), sk8.shape[0], _p(out)))
+        return out
+
+    def sign(self, sks, msg_idx, msgs32):
+        sk8 = sks if isinstance(sks, np.ndarray) else self._sk_limbs(sks)
+        sk8 = _c(sk8, np.uint32).reshape(-1, 8)
+        msg_idx = _c(msg_idx, np.uint32)
+        msgs = _c(msgs32, np.uint8).reshape(-1, 32)
+        out = np.zeros((sk8.shape[0], 96), dtype=np.uint8)
+        self._ck(self.lib.b2_sign(self.h, _p(sk8), _p(msg_idx), sk8.shape[0], _p(msgs), msgs.shape[0], _p(out)))
+        return out
+
+    def hash_to_g2(self, msgs32):
+        msgs = _c(msgs32, np.uint8).reshape(-1, 32)
+        out = np.zeros((msgs.shape[0], 96), dtype=np.uint8)
+        self._ck(self.lib.b2_hash_to_g2(self.h, _p(msgs), msgs.shape[0], _p(out)))
+        return out
+
+    # ------------------------------------------------------------------ fork choice
+    def latest_messages_reset(self):
+        self._ck(self.lib.b2_latest_messages_reset(self.h))
+
+    def latest_messages_load(self, epoch, block_idx, has_msg, equivocating):
+        e, b = _c(epoch, np.uint64), _c(block_idx, np.uint32)
+        h, q = _c(has_msg, np.uint8), _c(equivocating, np.uint8)
+        self._ck(self.lib.b2_latest_messages_load(self.h, _p(e), _p(b), _p(h), _p(q), e.shape[0]))
+
+    def latest_messages_read(self):
+        n = self.n_validators
+        e, b, h = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint8)
+        self._ck(self.lib.b2_latest_messages_read(self.h, _p(e), _p(b), _p(h), n))
+        return e, b, h
+
+    def latest_messages_update(self, members, off, bits, target_epoch, block_idx, accept=None):
+        members, off, bits, n_agg, stride = self._batch(members, off, bits)
+        te, bi = _c(target_epoch, np.uint64), _c(block_idx, np.uint32)
+        acc = _c(accept, np.uint8) if accept is not None else None
+        self._ck(self.lib.b2_latest_messages_update(self.h, _p(members), _p(off), _p(bits), stride, _p(te), _p(bi), _p(acc), n_agg))
+
+    def tree_load(self, parent, slot, roots32, leaf_viable):
+        parent, slot = _c(parent, np.uint32), _c(slot, np.uint64)
+        roots = _c(roots32, np.uint8).reshape(-1, 32)
+        viable = _c(leaf_viable, np.uint8)
+        n = parent.shape[0]
+        assert slot.shape == (n,) and roots.shape[0] == n and viable.shape == (n,)
+        self._ck(self.lib.b2_tree_load(self.h, _p(parent), _p(slot), _p(roots), _p(viable), n))
+        self.n_blocks = n
+
+    def get_weights(self, boost_idx: int = -1, boost_score: int = 0):
+        w = np.zeros(self.n_blocks, dtype=np.uint64)
+        self._ck(self.lib.b2_get_weights(self.h, int(boost_idx), int(boost_score), _p(w)))
+        return w
+
+    def get_head(self, justified_idx: int = 0, boost_idx: int = -1, boost_score: int = 0) -> int:
+        out = ctypes.c_uint32(0)
+        self._ck(self.lib.b2_get_head(self.h, int(justified_idx), int(boost_idx), int(boost_score), ctypes.byref(out)))
+        return int(out.value)
+
+    # ------------------------------------------------------------------ device-pointer entry points (torch CUDA tensors)
+    @staticmethod
+    def _stream():
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def aggregate_dev(self, d_sigs, d_seg_off, d_out96, d_status):
+        n_seg = d_seg_off.numel() - 1
+        n_sig = d_sigs.numel() // 96
+        self._ck(self.lib.b2_aggregate_dev(self.h, d_sigs.data_ptr(), d_seg_off.data_ptr(), n_seg, n_sig, d_out96.data_ptr(),
+                                           d_status.data_ptr(), self._stream()))
+
+    def fast_aggregate_verify_dev(self, d_members, d_off, d_bits, d_msgs, d_sigs, d_ok):
+        n_agg = d_off.numel() - 1
+        stride = d_bits.shape[1]
+        self._ck(self.lib.b2_fast_aggregate_verify_dev(self.h, d_members.data_ptr(), d_off.data_ptr(), d_bits.data_ptr(), stride,
+                                                       d_msgs.data_ptr(), d_sigs.data_ptr(), n_agg, d_ok.data_ptr(), self._stream()))
+
+    def latest_messages_update_dev(self, d_members, d_off, d_bits, d_target_epoch, d_block_idx, d_accept):
+        n_agg = d_off.numel() - 1
+        self._ck(self.lib.b2_latest_messages_update_dev(self.h, d_members.data_ptr(), d_off.data_ptr(), d_bits.data_ptr(), d_bits.shape[1],
+                                                        d_target_epoch.data_ptr(), d_block_idx.data_ptr(),
+                                                        d_accept.data_ptr() if d_accept is not None else None, n_agg, self._stream()))
+
+    def vote_weights_dev(self, d_votes):
+        self._ck(self.lib.b2_vote_weights_dev(self.h, d_votes.data_ptr(), self._stream()))
+
+    def head_from_votes_dev(self, d_votes, d_head, justified_idx=0, boost_idx=-1, boost_score=0, d_weight=None):
+        self._ck(self.lib.b2_head_from_votes_dev(self.h, d_votes.data_ptr(), int(justified_idx), int(boost_idx), int(boost_score),
+                                                 d_weight.data_ptr() if d_weight is not None else None, d_head.data_ptr(), self._stream()))

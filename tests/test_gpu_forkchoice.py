@@ -1,0 +1,91 @@
+"""GPU parity tests for the fork-choice half (K7-K9): latest-message table, per-block weights and
+head index against the numpy oracle (oracle/fast.py), at small sizes and at BASELINE.json's
+10 000 blocks / 2^20 validators."""
+import numpy as np
+import pytest
+
+import scenarios
+from oracle import fast
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pos_evolution_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _registry(eng, n, eff, active):
+    """fork choice never touches the pubkeys: load a registry of copies of one valid key."""
+    from oracle.bls12_381 import G1, g1_compress
+    pk = np.tile(np.frombuffer(g1_compress(G1), dtype=np.uint8), (n, 1))
+    eng.registry_load(pk, eff, active)
+
+
+@pytest.mark.parametrize("n_val,n_blk,seed", [(64, 1, 1), (64, 2, 2), (1000, 50, 3), (5000, 300, 4), (1 << 20, 10000, 4)])
+def test_weights_and_head(eng, n_val, n_blk, seed):
+    parent, slot, roots, leaf_viable = scenarios.fork_tree(n_blk, seed)
+    msg_block, has_msg, equiv, active, eff = scenarios.votes(n_val, n_blk, seed)
+    _registry(eng, n_val, eff, active)
+    eng.tree_load(parent, slot, roots, leaf_viable)
+    epoch = np.full(n_val, 3, dtype=np.uint64)
+    eng.latest_messages_load(epoch, msg_block, has_msg, equiv)
+    boost = fast.proposer_boost_score(eff, active, 32, 40)
+    for boost_idx in (-1, n_blk - 1, n_blk // 2):
+        w_ref = fast.ghost_weights(parent, msg_block, has_msg, eff, active, equiv, boost_idx, boost)
+        w = eng.get_weights(boost_idx, boost)
+        assert np.array_equal(w, w_ref)
+        keep = fast.ghost_viable(parent, leaf_viable)
+        assert eng.get_head(0, boost_idx, boost) == fast.ghost_head(parent, roots, keep, w_ref, 0)
+    # a second call must see a clean accumulator
+    assert np.array_equal(eng.get_weights(-1, 0), fast.ghost_weights(parent, msg_block, has_msg, eff, active, equiv, -1, 0))
+
+
+def test_head_tie_break_by_root(eng):
+    """all weights zero: the walk must follow the lexicographically highest root at every fork (ref :1114-1116)."""
+    parent, slot, roots, leaf_viable = scenarios.fork_tree(200, 9)
+    leaf_viable[:] = 1
+    n_val = 128
+    eff = np.full(n_val, 32 * 10**9, dtype=np.uint64)
+    _registry(eng, n_val, eff, np.ones(n_val, dtype=np.uint8))
+    eng.tree_load(parent, slot, roots, leaf_viable)
+    eng.latest_messages_reset()
+    keep = fast.ghost_viable(parent, leaf_viable)
+    w0 = np.zeros(200, dtype=np.uint64)
+    assert eng.get_head(0) == fast.ghost_head(parent, roots, keep, w0, 0)
+    assert eng.get_head(17) == fast.ghost_head(parent, roots, keep, w0, 17)
+
+
+def test_latest_messages_update_order_exact(eng):
+    rng = np.random.default_rng(12)
+    n_val, n_blk, n_agg, csize = 4096, 64, 96, 128
+    eff = np.full(n_val, 32 * 10**9, dtype=np.uint64)
+    _registry(eng, n_val, eff, np.ones(n_val, dtype=np.uint8))
+    msg_epoch = rng.integers(0, 3, size=n_val).astype(np.uint64)
+    msg_block = rng.integers(0, n_blk, size=n_val).astype(np.uint32)
+    has_msg = (rng.random(n_val) < 0.5).astype(np.uint8)
+    equiv = (rng.random(n_val) < 0.05).astype(np.uint8)
+    msg_block[has_msg == 0] = 0
+    eng.latest_messages_load(msg_epoch, msg_block, has_msg, equiv)
+    # overlapping committees on purpose: the same validator appears in several attestations of the batch
+    members = rng.integers(0, n_val, size=(n_agg, csize)).astype(np.uint32)
+    for a in range(n_agg):
+        members[a] = rng.permutation(n_val)[:csize]
+    off = np.arange(0, (n_agg + 1) * csize, csize, dtype=np.uint32)
+    bits = rng.integers(0, 256, size=(n_agg, csize // 8)).astype(np.uint8)
+    target_epoch = rng.integers(0, 5, size=n_agg).astype(np.uint64)
+    block_idx = rng.integers(0, n_blk, size=n_agg).astype(np.uint32)
+    accept = (rng.random(n_agg) < 0.8).astype(np.uint8)
+    for a in range(n_agg):                      # sequential oracle, list order
+        if not accept[a]:
+            continue
+        sel = [int(members[a, j]) for j in range(csize) if (bits[a, j >> 3] >> (j & 7)) & 1]
+        fast.lmd_update(msg_epoch, msg_block, has_msg, equiv, sel, int(target_epoch[a]), int(block_idx[a]))
+    eng.latest_messages_update(members.reshape(-1), off, bits, target_epoch, block_idx, accept)
+    e, b, h = eng.latest_messages_read()
+    assert np.array_equal(h, has_msg)
+    assert np.array_equal(e[h == 1], msg_epoch[h == 1])
+    assert np.array_equal(b[h == 1], msg_block[h == 1])
