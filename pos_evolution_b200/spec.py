@@ -1,0 +1,540 @@
+"""pyspec-signature host layer over the B200 engine.
+
+Keeps the names, argument meaning and error behaviour (AssertionError = invalid) of the functions
+quoted in /root/reference/pos-evolution.md, line numbers cited per function, so that it can stand
+in for the executable consensus spec on the path
+    process_attestation (:722) -> is_valid_indexed_attestation -> bls.FastAggregateVerify
+    on_attestation (:963/:1423) -> update_latest_messages (:1435) -> get_head (:1102).
+Python here only marshals: committee shuffling (SHA-256 via hashlib, vectorised numpy -- the GPU
+version is SURVEY.md section 8(f)-1), SSZ signing roots, participation-flag bookkeeping.  Signature
+aggregation/verification and the fork-choice weights/head run on the GPU through engine.Engine.
+This module never imports oracle/.
+"""
+import hashlib
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Set
+
+import numpy as np
+
+from .engine import Engine
+
+FAR_FUTURE_EPOCH = 2**64 - 1
+GENESIS_EPOCH = 0
+ZERO32 = bytes(32)
+DOMAIN_BEACON_PROPOSER = bytes.fromhex("00000000")
+DOMAIN_BEACON_ATTESTER = bytes.fromhex("01000000")
+TIMELY_SOURCE_FLAG_INDEX, TIMELY_TARGET_FLAG_INDEX, TIMELY_HEAD_FLAG_INDEX = 0, 1, 2
+PARTICIPATION_FLAG_WEIGHTS = [14, 26, 14]
+PROPOSER_WEIGHT = 8
+WEIGHT_DENOMINATOR = 64
+BASE_REWARD_FACTOR = 64
+
+
+@dataclass(frozen=True)
+class Preset:
+    name: str
+    SLOTS_PER_EPOCH: int
+    MAX_COMMITTEES_PER_SLOT: int
+    TARGET_COMMITTEE_SIZE: int
+    SHUFFLE_ROUND_COUNT: int
+    EPOCHS_PER_HISTORICAL_VECTOR: int
+    SLOTS_PER_HISTORICAL_ROOT: int
+    MAX_VALIDATORS_PER_COMMITTEE: int = 2048
+    MIN_ATTESTATION_INCLUSION_DELAY: int = 1
+    MIN_SEED_LOOKAHEAD: int = 1
+    MAX_EFFECTIVE_BALANCE: int = 32 * 10**9
+    EFFECTIVE_BALANCE_INCREMENT: int = 10**9
+    PROPOSER_SCORE_BOOST: int = 40
+
+
+MAINNET = Preset("mainnet", 32, 64, 128, 90, 65536, 8192)
+MINIMAL = Preset("minimal", 8, 4, 4, 10, 64, 64)
+
+
+# ----------------------------------------------------------------------------- containers
+@dataclass
+class Validator:                       # pos-evolution.md:36-45
+    pubkey: bytes
+    effective_balance: int
+    slashed: bool = False
+    activation_epoch: int = 0
+    exit_epoch: int = FAR_FUTURE_EPOCH
+
+
+@dataclass(frozen=True)
+class Checkpoint:                      # :219-221
+    epoch: int = 0
+    root: bytes = ZERO32
+
+
+@dataclass(frozen=True)
+class AttestationData:                 # :689-697
+    slot: int
+    index: int
+    beacon_block_root: bytes
+    source: Checkpoint
+    target: Checkpoint
+
+
+@dataclass
+class Attestation:                     # :714-717
+    aggregation_bits: List[bool]
+    data: AttestationData
+    signature: bytes
+
+
+@dataclass
+class IndexedAttestation:
+    attesting_indices: List[int]
+    data: AttestationData
+    signature: bytes
+
+
+@dataclass(frozen=True)
+class LatestMessage:                   # :287-289
+    epoch: int
+    root: bytes
+
+
+@dataclass
+class Fork:
+    previous_version: bytes = bytes(4)
+    current_version: bytes = bytes(4)
+    epoch: int = 0
+
+
+@dataclass
+class BeaconBlock:                     # :671-676 (fields fork choice reads)
+    slot: int
+    parent_root: bytes
+
+
+@dataclass
+class BeaconState:                     # :338-374 (fields the path reads/writes)
+    slot: int
+    fork: Fork
+    genesis_validators_root: bytes
+    validators: List[Validator]
+    balances: List[int]
+    randao_mixes: List[bytes]
+    block_roots: List[bytes]
+    previous_epoch_participation: List[int]
+    current_epoch_participation: List[int]
+    previous_justified_checkpoint: Checkpoint = Checkpoint()
+    current_justified_checkpoint: Checkpoint = Checkpoint()
+    finalized_checkpoint: Checkpoint = Checkpoint()
+
+
+@dataclass
+class Store:                           # :890-901
+    time: int
+    genesis_time: int
+    justified_checkpoint: Checkpoint
+    finalized_checkpoint: Checkpoint
+    best_justified_checkpoint: Checkpoint
+    proposer_boost_root: bytes
+    equivocating_indices: Set[int]
+    blocks: Dict[bytes, BeaconBlock] = field(default_factory=dict)
+    block_states: Dict[bytes, BeaconState] = field(default_factory=dict)
+    checkpoint_states: Dict[Checkpoint, BeaconState] = field(default_factory=dict)
+    latest_messages: Dict[int, LatestMessage] = field(default_factory=dict)
+
+
+# ----------------------------------------------------------------------------- SSZ-lite
+def sha256(b: bytes) -> bytes:
+    return hashlib.sha256(b).digest()
+
+
+def _u64_chunk(v: int) -> bytes:
+    return int(v).to_bytes(8, "little") + bytes(24)
+
+
+def _merkle(chunks):
+    n = 1
+    while n < len(chunks):
+        n *= 2
+    layer = list(chunks) + [ZERO32] * (n - len(chunks))
+    while len(layer) > 1:
+        layer = [sha256(layer[i] + layer[i + 1]) for i in range(0, len(layer), 2)]
+    return layer[0]
+
+
+def hash_tree_root_checkpoint(c: Checkpoint) -> bytes:
+    return _merkle([_u64_chunk(c.epoch), bytes(c.root)])
+
+
+def hash_tree_root_attestation_data(d: AttestationData) -> bytes:
+    return _merkle([_u64_chunk(d.slot), _u64_chunk(d.index), bytes(d.beacon_block_root),
+                    hash_tree_root_checkpoint(d.source), hash_tree_root_checkpoint(d.target)])
+
+
+def compute_domain(domain_type: bytes, fork_version: bytes, genesis_validators_root: bytes) -> bytes:
+    fork_data_root = _merkle([bytes(fork_version) + bytes(28), bytes(genesis_validators_root)])
+    return bytes(domain_type) + fork_data_root[:28]
+
+
+def integer_squareroot(n: int) -> int:
+    x, y = n, (n + 1) // 2
+    while y < x:
+        x, y = y, (y + n // y) // 2
+    return x
+
+
+def shuffle_permutation(n: int, seed: bytes, rounds: int) -> np.ndarray:
+    """perm[i] = compute_shuffled_index(i, n, seed) (:513-534) for every i at once: one pivot hash and
+    ceil(n/256) source hashes per round instead of two hashes per index per round."""
+    idx = np.arange(n, dtype=np.int64)
+    if n == 0:
+        return idx.astype(np.uint32)
+    nblk = (n + 255) // 256
+    for rnd in range(rounds):
+        r = bytes([rnd])
+        pivot = int.from_bytes(sha256(seed + r)[:8], "little") % n
+        src = b"".join(sha256(seed + r + blk.to_bytes(4, "little")) for blk in range(nblk))
+        bits = np.unpackbits(np.frombuffer(src, dtype=np.uint8), bitorder="little")
+        flip = (pivot + n - idx) % n
+        pos = np.maximum(idx, flip)
+        idx = np.where(bits[pos] == 1, flip, idx)
+    return idx.astype(np.uint32)
+
+
+def pack_bits(rows, stride=None) -> np.ndarray:
+    """list of bool lists -> uint8[n, stride], bit j of row a at byte j>>3, bit j&7 (SSZ Bitlist order)."""
+    n = max((len(r) for r in rows), default=0)
+    stride = stride or max(1, (n + 7) // 8)
+    out = np.zeros((len(rows), stride), dtype=np.uint8)
+    for a, r in enumerate(rows):
+        if len(r):
+            packed = np.packbits(np.asarray(r, dtype=np.uint8), bitorder="little")
+            out[a, :packed.shape[0]] = packed
+    return out
+
+
+class Spec:
+    """pyspec functions bound to a preset and a GPU engine."""
+
+    def __init__(self, preset: Preset = MAINNET, engine: Engine = None):
+        self.p = preset
+        self.engine = engine if engine is not None else Engine(0)
+        self._registry_key = None
+        self._committee_cache = {}
+
+    # ------------------------------------------------------------------ epochs / registry
+    def compute_epoch_at_slot(self, slot):
+        return slot // self.p.SLOTS_PER_EPOCH
+
+    def compute_start_slot_at_epoch(self, epoch):
+        return epoch * self.p.SLOTS_PER_EPOCH
+
+    def get_current_epoch(self, state):
+        return self.compute_epoch_at_slot(state.slot)
+
+    def get_previous_epoch(self, state):
+        cur = self.get_current_epoch(state)
+        return GENESIS_EPOCH if cur == GENESIS_EPOCH else cur - 1
+
+    @staticmethod
+    def is_active_validator(v, epoch):
+        return v.activation_epoch <= epoch < v.exit_epoch
+
+    def get_active_validator_indices(self, state, epoch):
+        return [i for i, v in enumerate(state.validators) if v.activation_epoch <= epoch < v.exit_epoch]
+
+    def get_total_active_balance(self, state):
+        e = self.get_current_epoch(state)
+        tot = sum(v.effective_balance for v in state.validators if v.activation_epoch <= e < v.exit_epoch)
+        return max(self.p.EFFECTIVE_BALANCE_INCREMENT, tot)
+
+    def get_randao_mix(self, state, epoch):
+        return state.randao_mixes[epoch % self.p.EPOCHS_PER_HISTORICAL_VECTOR]
+
+    def get_block_root_at_slot(self, state, slot):
+        assert slot < state.slot <= slot + self.p.SLOTS_PER_HISTORICAL_ROOT
+        return state.block_roots[slot % self.p.SLOTS_PER_HISTORICAL_ROOT]
+
+    def get_block_root(self, state, epoch):
+        return self.get_block_root_at_slot(state, self.compute_start_slot_at_epoch(epoch))
+
+    # ------------------------------------------------------------------ committees
+    def get_committee_count_per_slot(self, state, epoch):                      # :461-468
+        n_active = len(self.get_active_validator_indices(state, epoch))
+        return max(1, min(self.p.MAX_COMMITTEES_PER_SLOT, n_active // self.p.SLOTS_PER_EPOCH // self.p.TARGET_COMMITTEE_SIZE))
+
+    def get_seed(self, state, epoch, domain_type):                             # :481-486
+        mix = self.get_randao_mix(state, epoch + self.p.EPOCHS_PER_HISTORICAL_VECTOR - self.p.MIN_SEED_LOOKAHEAD - 1)
+        return sha256(domain_type + int(epoch).to_bytes(8, "little") + mix)
+
+    def compute_shuffled_index(self, index, index_count, seed):                # :513-534 (per-index form)
+        assert index < index_count
+        for rnd in range(self.p.SHUFFLE_ROUND_COUNT):
+            r = bytes([rnd])
+            pivot = int.from_bytes(sha256(seed + r)[0:8], "little") % index_count
+            flip = (pivot + index_count - index) % index_count
+            position = max(index, flip)
+            source = sha256(seed + r + (position // 256).to_bytes(4, "little"))
+            if (source[(position % 256) // 8] >> (position % 8)) & 1:
+                index = flip
+        return index
+
+    def compute_committee(self, indices, seed, index, count):                  # :495-504
+        n = len(indices)
+        start, end = (n * index) // count, (n * (index + 1)) // count
+        perm = self._permutation(n, seed)
+        return [indices[int(perm[i])] for i in range(start, end)]
+
+    def _permutation(self, n, seed):
+        key = (n, seed, self.p.SHUFFLE_ROUND_COUNT)
+        if key not in self._committee_cache:
+            if len(self._committee_cache) > 8:
+                self._committee_cache.clear()
+            self._committee_cache[key] = shuffle_permutation(n, seed, self.p.SHUFFLE_ROUND_COUNT)
+        return self._committee_cache[key]
+
+    def epoch_committees(self, state, epoch):
+        """All committees of ``epoch`` in array form: (members u32[n_active], off u32[count+1], committees_per_slot)."""
+        active = np.asarray(self.get_active_validator_indices(state, epoch), dtype=np.uint32)
+        cps = self.get_committee_count_per_slot(state, epoch)
+        seed = self.get_seed(state, epoch, DOMAIN_BEACON_ATTESTER)
+        n = len(active)
+        members = active[self._permutation(n, seed)]
+        count = cps * self.p.SLOTS_PER_EPOCH
+        off = np.array([(n * k) // count for k in range(count + 1)], dtype=np.uint32)
+        return members, off, cps
+
+    def get_beacon_committee(self, state, slot, index):                        # called at :729
+        epoch = self.compute_epoch_at_slot(slot)
+        members, off, cps = self.epoch_committees(state, epoch)
+        k = (slot % self.p.SLOTS_PER_EPOCH) * cps + index
+        return members[off[k]:off[k + 1]].tolist()
+
+    def compute_proposer_index(self, state, indices, seed):                    # :604-618
+        assert len(indices) > 0
+        i, total = 0, len(indices)
+        while True:
+            cand = indices[self.compute_shuffled_index(i % total, total, seed)]
+            random_byte = sha256(seed + (i // 32).to_bytes(8, "little"))[i % 32]
+            if state.validators[cand].effective_balance * 255 >= self.p.MAX_EFFECTIVE_BALANCE * random_byte:
+                return cand
+            i += 1
+
+    def get_beacon_proposer_index(self, state):                                # called at :754
+        epoch = self.get_current_epoch(state)
+        seed = sha256(self.get_seed(state, epoch, DOMAIN_BEACON_PROPOSER) + int(state.slot).to_bytes(8, "little"))
+        return self.compute_proposer_index(state, self.get_active_validator_indices(state, epoch), seed)
+
+    # ------------------------------------------------------------------ signing
+    def get_domain(self, state, domain_type, epoch=None):
+        epoch = self.get_current_epoch(state) if epoch is None else epoch
+        fv = state.fork.previous_version if epoch < state.fork.epoch else state.fork.current_version
+        return compute_domain(domain_type, fv, state.genesis_validators_root)
+
+    @staticmethod
+    def compute_signing_root(data: AttestationData, domain):
+        return _merkle([hash_tree_root_attestation_data(data), bytes(domain)])
+
+    # ------------------------------------------------------------------ registry on the device
+    def sync_registry(self, state):
+        """Upload state.validators once (pubkeys decompressed + KeyValidated on the GPU); later calls only
+        refresh balances/flags when the same validator list is seen again."""
+        key = (id(state.validators), len(state.validators))
+        n = len(state.validators)
+        epoch = self.get_current_epoch(state)
+        eff = np.fromiter((v.effective_balance for v in state.validators), dtype=np.uint64, count=n)
+        flags = np.fromiter(((1 if v.activation_epoch <= epoch < v.exit_epoch else 0) | (2 if v.slashed else 0)
+                             for v in state.validators), dtype=np.uint8, count=n)
+        if key != self._registry_key:
+            pk = np.frombuffer(b"".join(bytes(v.pubkey) for v in state.validators), dtype=np.uint8).reshape(n, 48)
+            self.engine.registry_load(pk, eff, flags)
+            self._registry_key = key
+        else:
+            self.engine.registry_update_balances(eff, flags)
+
+    # ------------------------------------------------------------------ indexed attestations (called at :736, :745, :975-976)
+    def get_attesting_indices(self, state, data, bits):
+        committee = self.get_beacon_committee(state, data.slot, data.index)
+        return set(v for i, v in enumerate(committee) if bits[i])
+
+    def get_indexed_attestation(self, state, attestation):
+        idx = self.get_attesting_indices(state, attestation.data, attestation.aggregation_bits)
+        return IndexedAttestation(sorted(idx), attestation.data, attestation.signature)
+
+    def is_valid_indexed_attestation(self, state, indexed):
+        return bool(self.are_valid_indexed_attestations(state, [indexed])[0])
+
+    def are_valid_indexed_attestations(self, state, indexed_list):
+        """Batched is_valid_indexed_attestation: one GPU FastAggregateVerify call for the whole list."""
+        if not indexed_list:
+            return np.zeros(0, dtype=np.uint8)
+        self.sync_registry(state)
+        n = len(state.validators)
+        members, off, msgs, sigs, structurally_ok = [], [0], [], [], []
+        for ia in indexed_list:
+            idx = list(ia.attesting_indices)
+            good = len(idx) > 0 and idx == sorted(set(idx)) and idx[-1] < n and len(bytes(ia.signature)) == 96
+            structurally_ok.append(good)
+            members += idx if good else []
+            off.append(len(members))
+            domain = self.get_domain(state, DOMAIN_BEACON_ATTESTER, ia.data.target.epoch)
+            msgs.append(self.compute_signing_root(ia.data, domain))
+            sigs.append(bytes(ia.signature) if len(bytes(ia.signature)) == 96 else bytes(96))
+        sizes = np.diff(np.asarray(off, dtype=np.int64))
+        stride = max(1, (int(sizes.max()) + 7) // 8)
+        bits = np.zeros((len(indexed_list), stride), dtype=np.uint8)
+        for a, s in enumerate(sizes):
+            full, rem = divmod(int(s), 8)
+            bits[a, :full] = 0xFF
+            if rem:
+                bits[a, full] = (1 << rem) - 1
+        ok = self.engine.fast_aggregate_verify(np.asarray(members, dtype=np.uint32), off, bits,
+                                               np.frombuffer(b"".join(msgs), dtype=np.uint8),
+                                               np.frombuffer(b"".join(sigs), dtype=np.uint8))
+        return ok & np.asarray(structurally_ok, dtype=np.uint8)
+
+    # ------------------------------------------------------------------ participation helpers (called at :733, :747-754)
+    def get_attestation_participation_flag_indices(self, state, data, inclusion_delay):
+        justified = state.current_justified_checkpoint if data.target.epoch == self.get_current_epoch(state) else state.previous_justified_checkpoint
+        matching_source = data.source == justified
+        matching_target = matching_source and data.target.root == self.get_block_root(state, data.target.epoch)
+        matching_head = matching_target and data.beacon_block_root == self.get_block_root_at_slot(state, data.slot)
+        assert matching_source
+        flags = []
+        if matching_source and inclusion_delay <= integer_squareroot(self.p.SLOTS_PER_EPOCH):
+            flags.append(TIMELY_SOURCE_FLAG_INDEX)
+        if matching_target and inclusion_delay <= self.p.SLOTS_PER_EPOCH:
+            flags.append(TIMELY_TARGET_FLAG_INDEX)
+        if matching_head and inclusion_delay == self.p.MIN_ATTESTATION_INCLUSION_DELAY:
+            flags.append(TIMELY_HEAD_FLAG_INDEX)
+        return flags
+
+    def get_base_reward_per_increment(self, state):
+        return self.p.EFFECTIVE_BALANCE_INCREMENT * BASE_REWARD_FACTOR // integer_squareroot(self.get_total_active_balance(state))
+
+    def get_base_reward(self, state, index):
+        return (state.validators[index].effective_balance // self.p.EFFECTIVE_BALANCE_INCREMENT) * self.get_base_reward_per_increment(state)
+
+    # ------------------------------------------------------------------ process_attestation (:722-754)
+    def _check_attestation(self, state, attestation):
+        data = attestation.data
+        assert data.target.epoch in (self.get_previous_epoch(state), self.get_current_epoch(state))     # :724
+        assert data.target.epoch == self.compute_epoch_at_slot(data.slot)                                # :725
+        assert data.slot + self.p.MIN_ATTESTATION_INCLUSION_DELAY <= state.slot <= data.slot + self.p.SLOTS_PER_EPOCH   # :726
+        assert data.index < self.get_committee_count_per_slot(state, data.target.epoch)                 # :727
+        committee = self.get_beacon_committee(state, data.slot, data.index)                              # :729
+        assert len(attestation.aggregation_bits) == len(committee)                                       # :730
+        flag_indices = self.get_attestation_participation_flag_indices(state, data, state.slot - data.slot)
+        return committee, flag_indices
+
+    def _apply_attestation(self, state, attestation, committee, flag_indices):
+        data = attestation.data
+        participation = state.current_epoch_participation if data.target.epoch == self.get_current_epoch(state) else state.previous_epoch_participation
+        per_inc = self.get_base_reward_per_increment(state)
+        numerator = 0
+        for v, bit in zip(committee, attestation.aggregation_bits):                                      # :745-749
+            if not bit:
+                continue
+            for flag_index, weight in enumerate(PARTICIPATION_FLAG_WEIGHTS):
+                if flag_index in flag_indices and not (participation[v] >> flag_index) & 1:
+                    participation[v] |= 1 << flag_index
+                    numerator += (state.validators[v].effective_balance // self.p.EFFECTIVE_BALANCE_INCREMENT) * per_inc * weight
+        denominator = (WEIGHT_DENOMINATOR - PROPOSER_WEIGHT) * WEIGHT_DENOMINATOR // PROPOSER_WEIGHT     # :752
+        state.balances[self.get_beacon_proposer_index(state)] += numerator // denominator                # :753-754
+
+    def process_attestation(self, state, attestation):
+        committee, flag_indices = self._check_attestation(state, attestation)
+        assert self.is_valid_indexed_attestation(state, self.get_indexed_attestation(state, attestation))   # :736 -> GPU
+        self._apply_attestation(state, attestation, committee, flag_indices)
+
+    def process_attestations(self, state, attestations):
+        """process_operations' attestation loop with ONE GPU verification batch.  Same observable behaviour as calling
+        process_attestation in order: the first invalid attestation raises AssertionError after its predecessors were applied."""
+        pre = []
+        for att in attestations:
+            try:
+                pre.append(self._check_attestation(state, att) + (self.get_indexed_attestation(state, att),))
+            except AssertionError:
+                pre.append(None)
+                break
+        verdicts = self.are_valid_indexed_attestations(state, [p[2] for p in pre if p is not None])
+        for k, att in enumerate(attestations):
+            assert k < len(pre) and pre[k] is not None and verdicts[k]
+            self._apply_attestation(state, att, pre[k][0], pre[k][1])
+
+    # ------------------------------------------------------------------ fork choice
+    def update_latest_messages(self, store, attesting_indices, attestation):   # :1435-1441 (host dict form)
+        target, root = attestation.data.target, attestation.data.beacon_block_root
+        for i in attesting_indices:
+            if i in store.equivocating_indices:
+                continue
+            if i not in store.latest_messages or target.epoch > store.latest_messages[i].epoch:
+                store.latest_messages[i] = LatestMessage(epoch=target.epoch, root=root)
+
+    def on_attestation(self, store, attestation, is_from_block=False):         # :963-979 / :1423-1428
+        target_state = store.checkpoint_states[attestation.data.target]
+        indexed = self.get_indexed_attestation(target_state, attestation)
+        assert self.is_valid_indexed_attestation(target_state, indexed)
+        self.update_latest_messages(store, indexed.attesting_indices, attestation)
+
+    def _store_arrays(self, store):
+        """Store (dicts) -> the array form of include/b200pos.h: blocks below the justified root in topological order."""
+        jroot = store.justified_checkpoint.root
+        children = {}
+        for r, b in store.blocks.items():
+            children.setdefault(b.parent_root, []).append(r)
+        order, queue = [], [jroot]
+        while queue:
+            r = queue.pop(0)
+            order.append(r)
+            queue.extend(children.get(r, []))
+        index = {r: i for i, r in enumerate(order)}
+        nb = len(order)
+        parent = np.zeros(nb, dtype=np.uint32)
+        slot = np.zeros(nb, dtype=np.uint64)
+        viable = np.ones(nb, dtype=np.uint8)
+        for i, r in enumerate(order):
+            b = store.blocks[r]
+            slot[i] = b.slot
+            if i:
+                parent[i] = index[b.parent_root]
+            if r not in children:
+                hs = store.block_states[r]
+                cj = store.justified_checkpoint.epoch == GENESIS_EPOCH or hs.current_justified_checkpoint == store.justified_checkpoint
+                cf = store.finalized_checkpoint.epoch == GENESIS_EPOCH or hs.finalized_checkpoint == store.finalized_checkpoint
+                viable[i] = 1 if (cj and cf) else 0
+        roots = np.frombuffer(b"".join(order), dtype=np.uint8).reshape(nb, 32)
+        return order, index, parent, slot, roots, viable
+
+    def _sync_store(self, store):
+        state = store.checkpoint_states[store.justified_checkpoint]
+        self.sync_registry(state)
+        order, index, parent, slot, roots, viable = self._store_arrays(store)
+        self.engine.tree_load(parent, slot, roots, viable)
+        n = len(state.validators)
+        epoch = np.zeros(n, dtype=np.uint64)
+        blk = np.zeros(n, dtype=np.uint32)
+        has = np.zeros(n, dtype=np.uint8)
+        for v, lm in store.latest_messages.items():
+            if v < n and lm.root in index:
+                epoch[v], blk[v], has[v] = lm.epoch, index[lm.root], 1
+        eq = np.zeros(n, dtype=np.uint8)
+        for v in store.equivocating_indices:
+            if v < n:
+                eq[v] = 1
+        self.engine.latest_messages_load(epoch, blk, has, eq)
+        boost_idx, boost_score = -1, 0
+        if store.proposer_boost_root != ZERO32 and store.proposer_boost_root in index:
+            active = [v for v in state.validators if self.is_active_validator(v, self.get_current_epoch(state))]
+            num = len(active)
+            avg = self.get_total_active_balance(state) // num
+            boost_score = (num // self.p.SLOTS_PER_EPOCH) * avg * self.p.PROPOSER_SCORE_BOOST // 100
+            boost_idx = index[store.proposer_boost_root]
+        return order, index, boost_idx, boost_score
+
+    def get_latest_attesting_balance(self, store, root):                       # called at :1116 (v1.2.0 form)
+        order, index, boost_idx, boost_score = self._sync_store(store)
+        return int(self.engine.get_weights(boost_idx, boost_score)[index[root]])
+
+    get_weight = get_latest_attesting_balance
+
+    def get_head(self, store):                                                 # :1102-1116
+        order, index, boost_idx, boost_score = self._sync_store(store)
+        return order[self.engine.get_head(0, boost_idx, boost_score)]

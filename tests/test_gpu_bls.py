@@ -143,7 +143,7 @@ def test_fast_aggregate_verify_vs_oracle(eng, world):
         scenarios.make_attestation(spec, state, 8, 0, corrupt="wrong_message"),
         scenarios.make_attestation(spec, state, 8, 1, corrupt="wrong_signer_set"),
         scenarios.make_attestation(spec, state, 8, 0, bits=[False] * 4),
-        scenarios.make_attestation(spec, state, 9, 1, bits=[False, False, True, False]),
+        scenarios.make_attestation(spec, state, 6, 1, bits=[False, False, True, False]),
     ]
     members, off, rows, msgs, sigs, expect = [], [0], [], [], [], []
     for att in atts:

@@ -1,0 +1,155 @@
+"""GPU tests of the pyspec-signature layer (pos_evolution_b200.spec / .bls) against the oracle's literal
+restatement on the minimal preset: same accept/reject decisions, same state mutation, same head root."""
+import copy
+
+import numpy as np
+import pytest
+
+import scenarios
+from oracle import bls_sig as OB
+from oracle import spec as OS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from pos_evolution_b200 import bls as PB
+    from pos_evolution_b200 import spec as PS
+    from pos_evolution_b200.engine import Engine
+    eng = Engine(0)
+    PB.use_engine(eng)
+    pks = scenarios.pubkeys(64)
+    ospec, ostate = scenarios.minimal_state(64, slot=9, pks=pks)
+    pspec = PS.Spec(PS.MINIMAL, engine=Engine(0))
+    return ospec, ostate, pspec, PS, PB, pks
+
+
+def _to_product(PS, x):
+    """oracle dataclasses -> product dataclasses (same field names)."""
+    if isinstance(x, OS.Checkpoint):
+        return PS.Checkpoint(x.epoch, x.root)
+    if isinstance(x, OS.AttestationData):
+        return PS.AttestationData(x.slot, x.index, x.beacon_block_root, _to_product(PS, x.source), _to_product(PS, x.target))
+    if isinstance(x, OS.Attestation):
+        return PS.Attestation(list(x.aggregation_bits), _to_product(PS, x.data), x.signature)
+    raise TypeError(x)
+
+
+def _state_to_product(PS, s):
+    return PS.BeaconState(
+        slot=s.slot, fork=PS.Fork(s.fork.previous_version, s.fork.current_version, s.fork.epoch),
+        genesis_validators_root=s.genesis_validators_root,
+        validators=[PS.Validator(v.pubkey, v.effective_balance, v.slashed, v.activation_epoch, v.exit_epoch) for v in s.validators],
+        balances=list(s.balances), randao_mixes=list(s.randao_mixes), block_roots=list(s.block_roots),
+        previous_epoch_participation=list(s.previous_epoch_participation), current_epoch_participation=list(s.current_epoch_participation),
+        previous_justified_checkpoint=_to_product(PS, s.previous_justified_checkpoint),
+        current_justified_checkpoint=_to_product(PS, s.current_justified_checkpoint),
+        finalized_checkpoint=_to_product(PS, s.finalized_checkpoint))
+
+
+def test_bls_facade_matches_oracle(env):
+    ospec, ostate, pspec, PS, PB, pks = env
+    m = b"\x42" * 32
+    sks = [scenarios.secret_key(i) for i in range(4)]
+    assert [PB.SkToPk(k) for k in sks] == pks[:4]
+    sigs = [PB.Sign(k, m) for k in sks]
+    assert sigs == [OB.Sign(k, m) for k in sks]
+    agg = PB.Aggregate(sigs)
+    assert agg == OB.Aggregate(sigs)
+    assert PB.FastAggregateVerify(pks[:4], m, agg) is True
+    assert PB.FastAggregateVerify(pks[:3], m, agg) is False
+    assert PB.FastAggregateVerify([], m, agg) is False
+    assert PB.FastAggregateVerify(pks[:4], m, b"\x00" * 96) is False
+    assert PB.FastAggregateVerify(pks[:4], m, b"short") is False
+    assert PB.Verify(pks[0], m, sigs[0]) is True and PB.Verify(pks[1], m, sigs[0]) is False
+    assert PB.KeyValidate(pks[0]) and not PB.KeyValidate(bytes([0xC0]) + bytes(47)) and not PB.KeyValidate(bytes(48))
+    with pytest.raises(ValueError):
+        PB.Aggregate([])
+    with pytest.raises(ValueError):
+        PB.Aggregate([sigs[0], bytes(96)])
+
+
+def test_process_attestation_matches_oracle(env):
+    ospec, ostate, pspec, PS, PB, pks = env
+    cases = [
+        (scenarios.make_attestation(ospec, ostate, 8, 0), True),
+        (scenarios.make_attestation(ospec, ostate, 8, 1, bits=[True, False, True, False]), True),
+        (scenarios.make_attestation(ospec, ostate, 5, 1), True),
+        (scenarios.make_attestation(ospec, ostate, 8, 0, corrupt="flip_bit"), False),
+        (scenarios.make_attestation(ospec, ostate, 8, 0, corrupt="wrong_message"), False),
+        (scenarios.make_attestation(ospec, ostate, 8, 1, corrupt="wrong_signer_set"), False),
+        (scenarios.make_attestation(ospec, ostate, 8, 0, bits=[False] * 4), False),
+        (scenarios.make_attestation(ospec, ostate, 8, 0, bits=[True] * 3), False),
+    ]
+    for att, valid in cases:
+        so = copy.deepcopy(ostate)
+        sp = _state_to_product(PS, ostate)
+        if valid:
+            ospec.process_attestation(so, att)
+            pspec.process_attestation(sp, _to_product(PS, att))
+            assert sp.balances == so.balances
+            assert sp.current_epoch_participation == so.current_epoch_participation
+            assert sp.previous_epoch_participation == so.previous_epoch_participation
+        else:
+            with pytest.raises(AssertionError):
+                ospec.process_attestation(so, att)
+            with pytest.raises(AssertionError):
+                pspec.process_attestation(sp, _to_product(PS, att))
+            assert sp.balances == ostate.balances and sp.current_epoch_participation == ostate.current_epoch_participation
+    # the batched form: all 16 aggregates of an epoch in one GPU call
+    so = copy.deepcopy(ostate)
+    so.slot = 16
+    so.block_roots = list(ostate.block_roots)
+    sp = _state_to_product(PS, so)
+    atts = [scenarios.make_attestation(ospec, so, s, i) for s in range(8, 16) for i in range(2)]
+    for a in atts:
+        ospec.process_attestation(so, a)
+    pspec.process_attestations(sp, [_to_product(PS, a) for a in atts])
+    assert sp.balances == so.balances and sp.current_epoch_participation == so.current_epoch_participation
+    assert sp.previous_epoch_participation == so.previous_epoch_participation
+
+
+def test_get_head_and_weight_match_oracle(env):
+    ospec, ostate, pspec, PS, PB, pks = env
+    n_blocks = 120
+    parent, slot, roots, leaf_viable = scenarios.fork_tree(n_blocks, 6)
+    rb = [bytes(r) for r in roots]
+    rng = np.random.default_rng(6)
+    ostate2 = copy.deepcopy(ostate)
+    ostate2.validators[7].exit_epoch = 0
+    pstate = _state_to_product(PS, ostate2)
+    has_child = set(int(p) for p in parent[1:])
+    for boost in (OS.ZERO32, rb[n_blocks - 1]):
+        oj, pj = OS.Checkpoint(1, rb[0]), PS.Checkpoint(1, rb[0])
+        ostore = OS.Store(0, 0, oj, oj, oj, boost, {3, 17})
+        pstore = PS.Store(0, 0, pj, pj, pj, boost, {3, 17})
+        for b in range(n_blocks):
+            pr = rb[parent[b]] if b else bytes(32)
+            ostore.blocks[rb[b]] = OS.BeaconBlock(int(slot[b]), pr)
+            pstore.blocks[rb[b]] = PS.BeaconBlock(int(slot[b]), pr)
+            obs, pbs = copy.copy(ostate2), copy.copy(pstate)
+            bad = b not in has_child and not leaf_viable[b]
+            obs.current_justified_checkpoint = OS.Checkpoint(0, b"\x01" * 32) if bad else oj
+            pbs.current_justified_checkpoint = PS.Checkpoint(0, b"\x01" * 32) if bad else pj
+            obs.finalized_checkpoint, pbs.finalized_checkpoint = oj, pj
+            ostore.block_states[rb[b]], pstore.block_states[rb[b]] = obs, pbs
+        ostore.checkpoint_states[oj], pstore.checkpoint_states[pj] = ostate2, pstate
+        for v in range(64):
+            if rng.random() < 0.9:
+                r = rb[int(n_blocks - 1 - min(n_blocks - 1, rng.geometric(0.05)))]
+                ostore.latest_messages[v] = OS.LatestMessage(1, r)
+                pstore.latest_messages[v] = PS.LatestMessage(1, r)
+        assert pspec.get_head(pstore) == ospec.get_head(ostore)
+        for b in (0, 1, n_blocks // 2, n_blocks - 1):
+            assert pspec.get_weight(pstore, rb[b]) == ospec.get_latest_attesting_balance(ostore, rb[b])
+    # on_attestation: verify on the GPU, then the host LMD table moves exactly like the oracle's
+    att = scenarios.make_attestation(ospec, ostate2, 8, 0, head_root=rb[5])
+    ostore.checkpoint_states[att.data.target] = ostate2
+    pstore.checkpoint_states[_to_product(PS, att.data.target)] = pstate
+    ospec.on_attestation(ostore, att)
+    pspec.on_attestation(pstore, _to_product(PS, att))
+    assert {v: (m.epoch, m.root) for v, m in pstore.latest_messages.items()} == {v: (m.epoch, m.root) for v, m in ostore.latest_messages.items()}
+    bad = scenarios.make_attestation(ospec, ostate2, 8, 0, corrupt="flip_bit")
+    with pytest.raises(AssertionError):
+        pspec.on_attestation(pstore, _to_product(PS, bad))
