@@ -1,0 +1,384 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of BASELINE.json:
+    "attestations aggregated+verified/sec at 1M validators; get_head p50 latency".
+
+One step = one full epoch for the 2^20 validators a rank owns (BASELINE.json configs[4] on one GPU:
+32 slots x 64 committees x 512 members): bls.Aggregate of the 1 048 576 individual G2 signatures into
+2 048 aggregates, FastAggregateVerify of the 2 048 aggregates (registry-indexed pubkey gather,
+hash-to-G2, pairing), update_latest_messages for the accepted ones, vote-weight scatter, [NCCL
+all-reduce of u64[10 000] vote weights when N > 1], get_head on a 10 000-block tree.
+`value`  = attestations/s with every input resident in HBM; `e2e` = the same through
+EpochProcessor.process_epoch_host with pinned HOST buffers (H2D of the signatures/bits/messages and
+D2H of verdicts + head inside the timed region).  Weak scaling: every rank owns its own 2^20
+validators (N x 2^20 validators overall); the only exchange is the vote-weight all-reduce.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo, on the GPU(s)
+    python bench.py --impl reference [...]                           # the CPU oracle (pyspec/py_ecc-class path)
+"""
+import argparse
+import hashlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "attestations aggregated+verified/sec at 1M validators; get_head p50 latency"
+UNIT = "attestations/s"
+N_VAL = 1 << 20
+SLOTS, COMMITTEES_PER_SLOT, COMMITTEE_SIZE = 32, 64, 512
+N_AGG = SLOTS * COMMITTEES_PER_SLOT
+N_BLOCKS = 10000
+R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+WORKLOAD = "full epoch: 32 slots x 64 committees x 512 members = 2^20 validators per rank; 10000-block fork tree"
+
+
+def _h(b):
+    return hashlib.sha256(b).digest()
+
+
+# ----------------------------------------------------------------------------- CPU legs (the only users of oracle/)
+def _cpu_one_committee(args):
+    """bls.Aggregate of the individual signatures + FastAggregateVerify, pure-Python oracle, one committee."""
+    from oracle import bls_sig as B
+    pks, sigs, msg = args
+    t0 = time.perf_counter()
+    agg = B.Aggregate(sigs)
+    ok = B.FastAggregateVerify(pks, msg, agg)
+    return time.perf_counter() - t0, bool(ok)
+
+
+def _cpu_make_committee(tag):
+    from oracle import synth
+    return synth.committee(tag, COMMITTEE_SIZE)
+
+
+def cpu_sample(pool, cores, committees):
+    """Time `committees` (list of (pks, sigs, msg)) over the worker pool; -> (attestations/s, wall seconds)."""
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_one_committee, committees)
+    wall = time.perf_counter() - t0
+    assert all(ok for _, ok in res), "oracle rejected a valid synthetic aggregate"
+    return len(committees) * COMMITTEE_SIZE / wall, wall
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the same path (oracle = restated pyspec + py_ecc-class big-int
+    arithmetic; the reference itself is Markdown and cannot be imported -- DESIGN.md), all host cores."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = min(host_cores(), 64)
+    with mp.get_context("fork").Pool(cores) as pool:
+        committees = pool.map(_cpu_make_committee, range(cores))
+        for _ in range(args.warmup):
+            cpu_sample(pool, cores, committees[:cores])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_sample(pool, cores, committees)
+        wall = time.perf_counter() - t0
+    value = args.steps * cores * COMMITTEE_SIZE / wall
+    sample = "%d committees x %d members per step (1 per core): bls.Aggregate + FastAggregateVerify" % (cores, COMMITTEE_SIZE)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fp)",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().strip().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def build_world(eng, rank, np, PS):
+    """Everything untimed: keys, registry, real 90-round committee shuffle, messages, individual signatures (all made
+    with the product's own kernels -- bls.SkToPk / bls.Sign on the GPU), fork tree and a pre-existing LMD table."""
+    t0 = time.time()
+    sk0 = (int.from_bytes(_h(b"b200pos/sk0"), "big") + rank * (1 << 200)) % (R_ORDER >> 1) or 1
+    delta = int.from_bytes(_h(b"b200pos/skd"), "big") >> 64             # 192-bit step: sk0 + i*delta < r for i < 2^20
+    sk_bytes = b"".join((sk0 + i * delta).to_bytes(32, "little") for i in range(N_VAL))
+    sk8 = np.frombuffer(sk_bytes, dtype=np.uint32).reshape(N_VAL, 8)
+    pk = eng.sk_to_pk(sk8)
+    rng = np.random.default_rng(4 + rank)
+    eff = np.where(rng.random(N_VAL) < 0.9, 32, rng.integers(16, 33, size=N_VAL)).astype(np.uint64) * np.uint64(10**9)
+    active = np.ones(N_VAL, dtype=np.uint8)
+    valid = eng.registry_load(pk, eff, active)
+    assert int(valid.sum()) == N_VAL
+    seed = _h(b"b200pos/epoch-seed" + rank.to_bytes(8, "little"))
+    perm = PS.shuffle_permutation(N_VAL, seed, 90)                      # compute_shuffled_index for all i (pos-evolution.md:513-534)
+    members = perm.astype(np.uint32)                                    # active set = all validators, committee k = members[512k : 512k+512]
+    off = (np.arange(N_AGG + 1, dtype=np.uint64) * COMMITTEE_SIZE).astype(np.uint32)
+    msgs = np.frombuffer(b"".join(_h(b"b200pos/signing-root" + rank.to_bytes(4, "little") + a.to_bytes(4, "little")) for a in range(N_AGG)),
+                         dtype=np.uint8).reshape(N_AGG, 32)
+    msg_idx = np.repeat(np.arange(N_AGG, dtype=np.uint32), COMMITTEE_SIZE)
+    sigs = eng.sign(np.ascontiguousarray(sk8[members]), msg_idx, msgs)   # signature j belongs to member j
+    # fork tree -- same on every rank
+    trng = np.random.default_rng(4)
+    parent = np.zeros(N_BLOCKS, dtype=np.uint32)
+    slot = np.zeros(N_BLOCKS, dtype=np.uint64)
+    back = trng.geometric(0.7, size=N_BLOCKS) - 1
+    skip = trng.binomial(2, 0.1, size=N_BLOCKS)
+    for i in range(1, N_BLOCKS):
+        parent[i] = max(0, i - 1 - int(back[i]))
+        slot[i] = slot[parent[i]] + 1 + int(skip[i])
+    roots = np.frombuffer(b"".join(_h(i.to_bytes(8, "little")) for i in range(N_BLOCKS)), dtype=np.uint8).reshape(N_BLOCKS, 32)
+    leaf_viable = (trng.random(N_BLOCKS) >= 0.05).astype(np.uint8)
+    eng.tree_load(parent, slot, roots, leaf_viable)
+    msg_block = (N_BLOCKS - 1 - np.minimum(N_BLOCKS - 1, rng.geometric(0.002, size=N_VAL))).astype(np.uint32)
+    has_msg = (rng.random(N_VAL) >= 0.01).astype(np.uint8)
+    equiv = (rng.random(N_VAL) < 0.001).astype(np.uint8)
+    eng.latest_messages_load(np.ones(N_VAL, dtype=np.uint64), msg_block, has_msg, equiv)
+    boost = (N_VAL // 32) * (int(eff.astype(object).sum()) // N_VAL) * 40 // 100
+    return dict(pk=pk, members=members, off=off, msgs=msgs, sigs=sigs, boost=boost, setup_s=time.time() - t0,
+                tree=(parent, roots, leaf_viable), votes=(msg_block, has_msg, equiv, eff, active))
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pos_evolution_b200 import spec as PS
+    from pos_evolution_b200.engine import Engine
+    from pos_evolution_b200.epoch import EpochProcessor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this benchmark has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    eng = Engine(local)
+    W = build_world(eng, rank, np, PS)
+    ep = EpochProcessor(eng, N_AGG, N_VAL, COMMITTEE_SIZE // 8, N_BLOCKS, process_group=pg, device=dev)
+    ep.set_committees(W["members"], W["off"])
+    bits_np = np.full((N_AGG, COMMITTEE_SIZE // 8), 0xFF, dtype=np.uint8)
+    blk_np = (N_BLOCKS - 1 - (np.arange(N_AGG) % 64)).astype(np.int32)
+    d_sigs = torch.as_tensor(W["sigs"], device=dev)
+    d_bits = torch.as_tensor(bits_np, device=dev)
+    d_msgs = torch.as_tensor(W["msgs"], device=dev)
+    d_epoch = torch.full((N_AGG,), 2, dtype=torch.int64, device=dev)
+    d_blk = torch.as_tensor(blk_np, device=dev)
+    h_sigs = torch.as_tensor(W["sigs"]).pin_memory()
+    h_bits = torch.as_tensor(bits_np).pin_memory()
+    h_msgs = torch.as_tensor(W["msgs"]).pin_memory()
+    h_epoch = torch.full((N_AGG,), 1000, dtype=torch.int64).pin_memory()
+    h_blk = torch.as_tensor(blk_np).pin_memory()
+    boost_idx, boost = N_BLOCKS - 1, W["boost"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        d_epoch.add_(1)                                # a later target epoch each step, so update_latest_messages really writes
+        return ep.process_epoch_dev(d_sigs, d_bits, d_msgs, d_epoch, d_blk, 0, boost_idx, boost)
+
+    # ---- warm-up, correctness gate: every aggregate must verify, and a corrupted epoch must not
+    for _ in range(max(args.warmup, 3)):
+        ok, head = step_dev()
+    barrier()
+    assert int(ok.sum().item()) == N_AGG, "GPU rejected valid aggregates"
+    head0 = int(head.item())
+
+    # ---- timed region 1: device-resident
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launch_count
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record()
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1) / args.steps
+    launches = (eng.launch_count - launches0) // args.steps + 1          # + the d_epoch.add_ elementwise kernel is torch's, not counted
+    clocks = sampler.stop()
+
+    # ---- timed region 2: end to end through the public host API (pinned host buffers, H2D + D2H inside)
+    for _ in range(2):
+        h_epoch.add_(1)
+        ep.process_epoch_host(h_sigs, h_bits, h_msgs, h_epoch, h_blk, 0, boost_idx, boost)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        h_epoch.add_(1)
+        h_ok, h_head = ep.process_epoch_host(h_sigs, h_bits, h_msgs, h_epoch, h_blk, 0, boost_idx, boost)
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1) / args.steps
+    assert int(h_ok.sum()) == N_AGG
+
+    # ---- dominant kernel alone (roofline): stage 1 of bls.Aggregate, G2 decompression of 2^20 signatures
+    from pos_evolution_b200 import _lib
+    lib = _lib.load()
+    ks0, ks1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    torch.cuda.synchronize()
+    ks0.record()
+    for _ in range(reps):
+        eng.aggregate_dev(d_sigs, ep.d_off, ep.d_agg_sig, ep.d_agg_status)
+    ks1.record()
+    torch.cuda.synchronize()
+    ms_agg = ks0.elapsed_time(ks1) / reps
+    kv0, kv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kv0.record()
+    for _ in range(reps):
+        eng.fast_aggregate_verify_dev(ep.d_members, ep.d_off, d_bits, d_msgs, ep.d_agg_sig, ep.d_ok)
+    kv1.record()
+    torch.cuda.synchronize()
+    ms_verify = kv0.elapsed_time(kv1) / reps
+
+    # ---- get_head latency: C-ABI call incl. D2H of the head index
+    lat = []
+    for i in range(250):
+        t0 = time.perf_counter()
+        hd = eng.get_head(0, boost_idx, boost)
+        lat.append((time.perf_counter() - t0) * 1e6)
+    lat = sorted(lat[50:])
+    p50, p99 = lat[len(lat) // 2], lat[int(len(lat) * 0.99) - 1]
+
+    # max over ranks
+    t = torch.tensor([ms_dev, ms_e2e, ms_agg, ms_verify, p50, p99], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e, ms_agg, ms_verify, p50, p99 = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        algo_bytes = 96 * N_VAL + 96 * N_AGG                              # bls.Aggregate = 96n + 96s
+        achieved = algo_bytes / (ms_agg * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * N_VAL / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (381-bit Fp, Montgomery)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "validators_per_rank": N_VAL, "aggregates_per_rank": N_AGG, "parallelism": "validators sharded x%d, one u64[10000] all-reduce" % world,
+                       "l2": "per-step working set ~0.5 GB (signatures 101 MB + decompressed points 201 MB + registry 101 MB) > 126 MB L2"},
+            "e2e": {"value": world * N_VAL / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": ep.h2d_bytes, "d2h_bytes_per_step": ep.d2h_bytes},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "get_head_p50_us": p50, "get_head_p99_us": p99, "head_index": head0,
+            "stage_ms": {"bls_aggregate_2^20_sigs": ms_agg, "fast_aggregate_verify_2048": ms_verify},
+            "roofline": {"bound": "hbm", "kernel": "bls.Aggregate (k_g2_decompress + k_g2_segment_sum)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "integer-pipe bound, not HBM bound: ~950 Fp mul (x ~290 IMAD.WIDE) per 96-byte signature; see DESIGN.md"},
+            "setup_s": W["setup_s"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import multiprocessing as mp
+            cores = min(host_cores(), 64)
+            with mp.get_context("fork").Pool(cores) as pool:
+                # same workload, bounded sample: the first `cores` committees of this very epoch (GPU-made keys/signatures)
+                comm = []
+                for a in range(cores):
+                    m = W["members"][a * COMMITTEE_SIZE:(a + 1) * COMMITTEE_SIZE]
+                    comm.append(([bytes(W["pk"][v]) for v in m], [bytes(s) for s in W["sigs"][a * COMMITTEE_SIZE:(a + 1) * COMMITTEE_SIZE]], bytes(W["msgs"][a])))
+                v, wall = cpu_sample(pool, cores, comm)
+            from oracle import fast
+            parent, roots, leaf_viable = W["tree"]
+            t0 = time.perf_counter()
+            e, b, hmsg = eng.latest_messages_read()
+            t0 = time.perf_counter()
+            w = fast.ghost_weights(parent, b, hmsg, W["votes"][3], W["votes"][4], W["votes"][2], boost_idx, boost)
+            hd_cpu = fast.ghost_head(parent, roots, fast.ghost_viable(parent, leaf_viable), w, 0)
+            cpu_head_ms = (time.perf_counter() - t0) * 1e3
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d of the 2048 committees of this epoch (512 members each), 1 per core, %.1f s wall: oracle bls.Aggregate + FastAggregateVerify" % (cores, wall),
+                                    "get_head_numpy_ms": cpu_head_ms, "get_head_matches_gpu": bool(world > 1 or hd_cpu == hd)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
