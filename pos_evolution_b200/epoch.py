@@ -37,8 +37,9 @@ class EpochProcessor:
         self.d_msgs = torch.zeros((n_agg, 32), dtype=torch.uint8, device=d)
         self.d_target_epoch = torch.zeros(n_agg, dtype=torch.int64, device=d)
         self.d_block_idx = torch.zeros(n_agg, dtype=torch.int32, device=d)
-        self.h_ok = torch.zeros(n_agg, dtype=torch.uint8).pin_memory()
-        self.h_head = torch.zeros(1, dtype=torch.int32).pin_memory()
+        pin = torch.cuda.is_available()
+        self.h_ok = torch.zeros(n_agg, dtype=torch.uint8, pin_memory=pin)
+        self.h_head = torch.zeros(1, dtype=torch.int32, pin_memory=pin)
 
     def set_committees(self, members, off):
         """members u32[n_sig] (committee order), off u32[n_agg+1]; signature j belongs to member j."""
