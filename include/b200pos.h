@@ -86,6 +86,14 @@ int b2_sign(b2_ctx* ctx, const uint32_t* sk8, const uint32_t* msg_idx, uint64_t 
 /* H(m) compressed, for tests (hash_to_G2 with the POP ciphersuite tag) */
 int b2_hash_to_g2(b2_ctx* ctx, const uint8_t* msg32, uint32_t n_msg, uint8_t* out96);
 
+/* ---- committees: compute_committee / compute_shuffled_index (pos-evolution.md:495-534) for a whole epoch.
+ * members_out[i] = active[compute_shuffled_index(i, n_active, seed)] (active == NULL: identity), so committee k of
+ * `count` is members_out[n*k/count .. n*(k+1)/count).  SHA-256 and the swap-or-not rounds run on the GPU. */
+int b2_shuffle_committees(b2_ctx* ctx, const uint8_t* seed32, const uint32_t* active, uint32_t n_active, uint32_t rounds,
+                          uint32_t* members_out);
+int b2_shuffle_committees_dev(b2_ctx* ctx, const uint8_t* d_seed32, const uint32_t* d_active, uint32_t n_active, uint32_t rounds,
+                              uint32_t* d_members_out, void* stream);
+
 /* ---- fork choice --------------------------------------------------------------------------------
  * Store.latest_messages (pos-evolution.md:901) lives on the device as (epoch, block index) per validator. */
 int b2_latest_messages_reset(b2_ctx* ctx);
@@ -114,6 +122,12 @@ int b2_aggregate_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_
 int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                                  uint32_t bits_stride, const uint8_t* d_msg32, const uint8_t* d_sig96, uint32_t n_agg,
                                  uint8_t* d_ok_out, void* stream);
+/* One epoch of this rank in one call: bls.Aggregate per committee (segment a = signatures [off[a], off[a+1]), one per member, in
+ * committee order) -> FastAggregateVerify of the aggregates -> update_latest_messages for the accepted ones.  The pubkey/hash half
+ * of the verification is overlapped with the signature decompression on side streams. */
+int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
+                 uint32_t bits_stride, const uint8_t* d_msg32, const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg,
+                 uint64_t n_sig, uint8_t* d_agg_sig96, int32_t* d_agg_status, uint8_t* d_ok_out, void* stream);
 int b2_latest_messages_update_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                                   uint32_t bits_stride, const uint64_t* d_target_epoch, const uint32_t* d_block_idx,
                                   const uint8_t* d_accept, uint32_t n_agg, void* stream);

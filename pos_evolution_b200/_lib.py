@@ -37,6 +37,8 @@ SIGNATURES = {
     "b2_sk_to_pk": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
     "b2_sign": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p]),
     "b2_hash_to_g2": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b2_shuffle_committees": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_void_p]),
+    "b2_shuffle_committees_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_void_p, c_void_p]),
     "b2_latest_messages_reset": (c_int, [c_void_p]),
     "b2_latest_messages_load": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64]),
     "b2_latest_messages_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64]),
@@ -47,6 +49,8 @@ SIGNATURES = {
     "b2_aggregate_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p]),
     "b2_fast_aggregate_verify_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]),
     "b2_latest_messages_update_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "b2_epoch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_uint64,
+                             c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2_vote_weights_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b2_head_from_votes_dev": (c_int, [c_void_p, c_void_p, c_uint32, c_int32, c_uint64, c_void_p, c_void_p, c_void_p]),
     "b2_tree_size": (c_uint32, [c_void_p]),

@@ -41,7 +41,7 @@ struct b2_ctx {
     uint32_t* d_head = nullptr;
     // scratch
     dbuf sc_pkjac, sc_pkst, sc_haff, sc_hflag, sc_saff, sc_sflag, sc_f, sc_g2aff, sc_g2st, sc_rec, sc_val;
-    dbuf in_a, in_b, in_c, in_d, in_e, in_f, in_g, out_a, out_b;
+    dbuf in_a, in_b, in_c, in_d, in_e, in_f, in_g, out_a, out_b, sc_shuf, sc_pivot;
 };
 
 static int fail_cuda(b2_ctx* c, cudaError_t e, const char* what) {
@@ -104,8 +104,12 @@ int b2_init(int device, b2_ctx** out) {
         delete ctx;
         return B2_ENODEVICE;
     }
-    cudaError_t e = cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->s_aux[i], cudaStreamNonBlocking);
+    // side streams get the highest priority: their kernels are small and latency-bound and must be scheduled as soon
+    // as SM resources free up while a grid-filling kernel (signature decompression) occupies the main stream
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&ctx->s_main, cudaStreamNonBlocking, prio_lo);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithPriority(&ctx->s_aux[i], cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -128,7 +132,7 @@ void b2_destroy(b2_ctx* ctx) {
         if (p) cudaFree(p);
     dbuf* bufs[] = {&ctx->sc_pkjac, &ctx->sc_pkst, &ctx->sc_haff, &ctx->sc_hflag, &ctx->sc_saff, &ctx->sc_sflag, &ctx->sc_f,
                     &ctx->sc_g2aff, &ctx->sc_g2st, &ctx->sc_rec, &ctx->sc_val, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d,
-                    &ctx->in_e, &ctx->in_f, &ctx->in_g, &ctx->out_a, &ctx->out_b};
+                    &ctx->in_e, &ctx->in_f, &ctx->in_g, &ctx->out_a, &ctx->out_b, &ctx->sc_shuf, &ctx->sc_pivot};
     for (dbuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
@@ -288,35 +292,65 @@ int b2_aggregate(b2_ctx* ctx, const uint8_t* sig96, const uint32_t* seg_off, uin
 }
 
 // ------------------------------------------------------------------------------------------ FastAggregateVerify
-// Given aggregated pubkeys in sc_pkjac / sc_pkst: hash, signature check, two Miller loops, final exp.
-// H(m) and the signature check do not depend on the pubkey aggregation: they run on two side
-// streams while the caller's stream aggregates, then join for the pairing.
-static int verify_tail(b2_ctx* ctx, const uint8_t* d_msg32, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s, bool fork_done) {
+// Verification pipeline on three streams.  Nothing on the two side streams depends on the signatures:
+//   aux0: K4 hash-to-G2
+//   aux1: K2 pubkey gather+aggregate (or the explicit-key variant), then [after aux0] the Miller loop e(PK_agg, H(m))
+//   main: signature decompression + subgroup check, Miller loop e(-g1, sig), [join aux1] final exponentiation.
+// verify_fork() enqueues the side work forked from the *current* position of the caller's stream, verify_main()
+// the signature half; b2_epoch_dev calls verify_fork() BEFORE it enqueues the epoch's signature aggregation so that
+// the side work overlaps with it.
+struct pk_source {
+    const uint32_t *d_members, *d_off;
+    const uint8_t* d_bits;
+    uint32_t bits_stride;
+    const uint8_t* d_pk48;      // explicit-key form when non-null (d_off = pk offsets)
+    uint64_t n_pk;
+};
+static int verify_fork(b2_ctx* ctx, const pk_source& P, const uint8_t* d_msg32, uint32_t n_agg, cudaStream_t s) {
     int rc;
     if ((rc = ensure(ctx, ctx->sc_haff, (size_t)n_agg * 192)) || (rc = ensure(ctx, ctx->sc_hflag, n_agg)) ||
         (rc = ensure(ctx, ctx->sc_saff, (size_t)n_agg * 192)) || (rc = ensure(ctx, ctx->sc_sflag, n_agg)) ||
-        (rc = ensure(ctx, ctx->sc_f, (size_t)n_agg * 2 * 576)))
+        (rc = ensure(ctx, ctx->sc_f, (size_t)n_agg * 2 * 576)) || (rc = ensure(ctx, ctx->sc_pkjac, (size_t)n_agg * 144)) ||
+        (rc = ensure(ctx, ctx->sc_pkst, n_agg)))
         return rc;
-    (void)fork_done;
+    if (P.d_pk48 && ((rc = ensure(ctx, ctx->sc_rec, P.n_pk * 96 + 16)) || (rc = ensure(ctx, ctx->sc_val, P.n_pk + 16)))) return rc;
     CK(cudaEventRecord(ctx->ev_fork, s));
     CK(cudaStreamWaitEvent(ctx->s_aux[0], ctx->ev_fork, 0));
     CK(cudaStreamWaitEvent(ctx->s_aux[1], ctx->ev_fork, 0));
     k_hash_to_g2<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->sc_hflag.p);
     CKL(ctx);
-    k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[1]>>>(d_sig96, n_agg, (uint32_t*)ctx->sc_saff.p, (uint8_t*)ctx->sc_sflag.p);
-    CKL(ctx);
     CK(cudaEventRecord(ctx->ev_join[0], ctx->s_aux[0]));
+    if (P.d_pk48) {
+        if (P.n_pk) {
+            k_g1_decompress_validate<<<blocks_for(P.n_pk, 128), 128, 0, ctx->s_aux[1]>>>(P.d_pk48, P.n_pk, (uint32_t*)ctx->sc_rec.p, (uint8_t*)ctx->sc_val.p);
+            CKL(ctx);
+        }
+        k_g1_segment_sum<<<n_agg, 128, 0, ctx->s_aux[1]>>>((const uint32_t*)ctx->sc_rec.p, (const uint8_t*)ctx->sc_val.p, P.d_off, n_agg,
+                                                          (uint32_t*)ctx->sc_pkjac.p, (uint8_t*)ctx->sc_pkst.p);
+        CKL(ctx);
+    } else {
+        k_g1_aggregate<<<n_agg, 128, 0, ctx->s_aux[1]>>>(ctx->d_records, ctx->d_valid, P.d_members, P.d_off, P.d_bits, P.bits_stride, n_agg,
+                                                        (uint32_t*)ctx->sc_pkjac.p, (uint8_t*)ctx->sc_pkst.p);
+        CKL(ctx);
+    }
+    CK(cudaStreamWaitEvent(ctx->s_aux[1], ctx->ev_join[0], 0));
+    k_miller<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[1]>>>((const uint32_t*)ctx->sc_pkjac.p, (const uint8_t*)ctx->sc_pkst.p,
+                                                             (const uint32_t*)ctx->sc_haff.p, (const uint8_t*)ctx->sc_hflag.p,
+                                                             (const uint32_t*)ctx->sc_saff.p, (const uint8_t*)ctx->sc_sflag.p, n_agg,
+                                                             (uint32_t*)ctx->sc_f.p, 1);
+    CKL(ctx);
     CK(cudaEventRecord(ctx->ev_join[1], ctx->s_aux[1]));
     return B2_OK;
 }
-static int verify_join(b2_ctx* ctx, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s) {
-    CK(cudaStreamWaitEvent(s, ctx->ev_join[0], 0));
-    CK(cudaStreamWaitEvent(s, ctx->ev_join[1], 0));
-    k_miller<<<blocks_for(2ull * n_agg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_pkjac.p, (const uint8_t*)ctx->sc_pkst.p,
-                                                        (const uint32_t*)ctx->sc_haff.p, (const uint8_t*)ctx->sc_hflag.p,
-                                                        (const uint32_t*)ctx->sc_saff.p, (const uint8_t*)ctx->sc_sflag.p, n_agg,
-                                                        (uint32_t*)ctx->sc_f.p);
+static int verify_main(b2_ctx* ctx, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s) {
+    k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, s>>>(d_sig96, n_agg, (uint32_t*)ctx->sc_saff.p, (uint8_t*)ctx->sc_sflag.p);
     CKL(ctx);
+    k_miller<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_pkjac.p, (const uint8_t*)ctx->sc_pkst.p,
+                                                  (const uint32_t*)ctx->sc_haff.p, (const uint8_t*)ctx->sc_hflag.p,
+                                                  (const uint32_t*)ctx->sc_saff.p, (const uint8_t*)ctx->sc_sflag.p, n_agg,
+                                                  (uint32_t*)ctx->sc_f.p, 2);
+    CKL(ctx);
+    CK(cudaStreamWaitEvent(s, ctx->ev_join[1], 0));
     k_final_verdict<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_f.p, (const uint8_t*)ctx->sc_pkst.p,
                                                         (const uint8_t*)ctx->sc_sflag.p, n_agg, d_ok);
     CKL(ctx);
@@ -330,9 +364,28 @@ int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const u
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if ((rc = verify_tail(ctx, d_msg32, d_sig96, n_agg, d_ok_out, s, false))) return rc;
-    if ((rc = g1_aggregate_dev(ctx, d_members, d_off, d_bits, bits_stride, n_agg, s))) return rc;
-    return verify_join(ctx, n_agg, d_ok_out, s);
+    pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
+    if ((rc = verify_fork(ctx, P, d_msg32, n_agg, s))) return rc;
+    return verify_main(ctx, d_sig96, n_agg, d_ok_out, s);
+}
+
+// One epoch for the validators of this rank: per-committee bls.Aggregate of the individual signatures, FastAggregateVerify
+// of the aggregates, update_latest_messages for the accepted ones.  The signature-independent half of the verification
+// is forked first so it overlaps with the (grid-filling) signature decompression.
+int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
+                 uint32_t bits_stride, const uint8_t* d_msg32, const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg,
+                 uint64_t n_sig, uint8_t* d_agg_sig96, int32_t* d_agg_status, uint8_t* d_ok_out, void* stream) {
+    REQUIRE(ctx && d_sig96 && d_members && d_off && d_bits && d_msg32 && d_target_epoch && d_block_idx && d_agg_sig96 && d_agg_status && d_ok_out &&
+                n_agg > 0 && bits_stride > 0, "epoch_dev: bad arguments");
+    REQUIRE(ctx->n_val > 0, "epoch_dev: registry not loaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
+    if ((rc = verify_fork(ctx, P, d_msg32, n_agg, s))) return rc;
+    if ((rc = b2_aggregate_dev(ctx, d_sig96, d_off, n_agg, n_sig, d_agg_sig96, d_agg_status, s))) return rc;
+    if ((rc = verify_main(ctx, d_agg_sig96, n_agg, d_ok_out, s))) return rc;
+    return b2_latest_messages_update_dev(ctx, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_ok_out, n_agg, s);
 }
 
 int b2_fast_aggregate_verify(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
@@ -377,15 +430,9 @@ int b2_fast_aggregate_verify_pks(b2_ctx* ctx, const uint8_t* pk48, const uint32_
     CK(cudaMemcpyAsync(ctx->in_b.p, pk_off, (size_t)(n_agg + 1) * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->in_d.p, sig96, (size_t)n_agg * 96, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->in_e.p, msg32, (size_t)n_agg * 32, cudaMemcpyHostToDevice, s));
-    if ((rc = verify_tail(ctx, (const uint8_t*)ctx->in_e.p, (const uint8_t*)ctx->in_d.p, n_agg, (uint8_t*)ctx->out_a.p, s, false))) return rc;
-    if (n_pk) {
-        k_g1_decompress_validate<<<blocks_for(n_pk, 128), 128, 0, s>>>((const uint8_t*)ctx->in_a.p, n_pk, (uint32_t*)ctx->sc_rec.p, (uint8_t*)ctx->sc_val.p);
-        CKL(ctx);
-    }
-    k_g1_segment_sum<<<n_agg, 128, 0, s>>>((const uint32_t*)ctx->sc_rec.p, (const uint8_t*)ctx->sc_val.p, (const uint32_t*)ctx->in_b.p, n_agg,
-                                           (uint32_t*)ctx->sc_pkjac.p, (uint8_t*)ctx->sc_pkst.p);
-    CKL(ctx);
-    if ((rc = verify_join(ctx, n_agg, (uint8_t*)ctx->out_a.p, s))) return rc;
+    pk_source P = {nullptr, (const uint32_t*)ctx->in_b.p, nullptr, 0, (const uint8_t*)ctx->in_a.p, n_pk};
+    if ((rc = verify_fork(ctx, P, (const uint8_t*)ctx->in_e.p, n_agg, s))) return rc;
+    if ((rc = verify_main(ctx, (const uint8_t*)ctx->in_d.p, n_agg, (uint8_t*)ctx->out_a.p, s))) return rc;
     std::vector<uint8_t> tok(n_agg);
     CK(cudaMemcpyAsync(tok.data(), ctx->out_a.p, n_agg, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -443,6 +490,45 @@ int b2_sign(b2_ctx* ctx, const uint32_t* sk8, const uint32_t* msg_idx, uint64_t 
     k_sign<<<blocks_for(n, 64), 64, 0, s>>>((const uint32_t*)ctx->in_f.p, (const uint32_t*)ctx->in_g.p, n, (const uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->out_a.p);
     CKL(ctx);
     CK(cudaMemcpyAsync(sig96_out, ctx->out_a.p, n * 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ committee shuffle
+int b2_shuffle_committees_dev(b2_ctx* ctx, const uint8_t* d_seed32, const uint32_t* d_active, uint32_t n_active, uint32_t rounds,
+                              uint32_t* d_members_out, void* stream) {
+    REQUIRE(ctx && d_seed32 && d_members_out && rounds <= 255, "shuffle_committees_dev: bad arguments");
+    if (n_active == 0) return B2_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t nblk = (n_active + 255) / 256;
+    int rc;
+    if ((rc = ensure(ctx, ctx->sc_shuf, (size_t)rounds * nblk * 32 + 16)) || (rc = ensure(ctx, ctx->sc_pivot, (size_t)rounds * 8 + 16))) return rc;
+    if (rounds) {
+        k_shuffle_sources<<<blocks_for((uint64_t)rounds * nblk, 128), 128, 0, s>>>(d_seed32, n_active, rounds, nblk, (uint8_t*)ctx->sc_shuf.p,
+                                                                                  (unsigned long long*)ctx->sc_pivot.p);
+        CKL(ctx);
+    }
+    k_shuffle_apply<<<blocks_for(n_active, 256), 256, 0, s>>>(n_active, rounds, nblk, (const uint8_t*)ctx->sc_shuf.p,
+                                                             (const unsigned long long*)ctx->sc_pivot.p, d_active, d_members_out);
+    CKL(ctx);
+    return B2_OK;
+}
+
+int b2_shuffle_committees(b2_ctx* ctx, const uint8_t* seed32, const uint32_t* active, uint32_t n_active, uint32_t rounds, uint32_t* members_out) {
+    REQUIRE(ctx && seed32 && members_out && rounds <= 255, "shuffle_committees: bad arguments");
+    if (n_active == 0) return B2_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_e, 32)) || (rc = ensure(ctx, ctx->in_a, (size_t)n_active * 4)) || (rc = ensure(ctx, ctx->out_a, (size_t)n_active * 4)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->in_e.p, seed32, 32, cudaMemcpyHostToDevice, s));
+    if (active) CK(cudaMemcpyAsync(ctx->in_a.p, active, (size_t)n_active * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = b2_shuffle_committees_dev(ctx, (const uint8_t*)ctx->in_e.p, active ? (const uint32_t*)ctx->in_a.p : nullptr, n_active, rounds,
+                                        (uint32_t*)ctx->out_a.p, s)))
+        return rc;
+    CK(cudaMemcpyAsync(members_out, ctx->out_a.p, (size_t)n_active * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return B2_OK;
 }

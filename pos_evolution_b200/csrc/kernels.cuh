@@ -179,13 +179,20 @@ __device__ __forceinline__ g2_aff load_g2_aff(const uint32_t* p) {
     for (int k = 0; k < 48; k++) w[k] = p[k];
     return r;
 }
-// thread 2a: miller(PK_agg[a], H(m_a));  thread 2a+1: miller(-g1, sig_a)
+// value 2a: miller(PK_agg[a], H(m_a));  value 2a+1: miller(-g1, sig_a).  mode 0: one launch computes both (thread t
+// <-> value t); mode 1 / 2: only the pubkey / signature half (thread a), so that the pubkey half can run on a side
+// stream while the signatures of the epoch are still being aggregated.
 __global__ void __launch_bounds__(32) k_miller(const uint32_t* __restrict__ pk_jac, const uint8_t* __restrict__ pk_status,
                                                 const uint32_t* __restrict__ h_aff, const uint8_t* __restrict__ hflag,
                                                 const uint32_t* __restrict__ s_aff, const uint8_t* __restrict__ sflag, uint32_t n_agg,
-                                                uint32_t* f_out) {
+                                                uint32_t* f_out, int mode) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n_agg) return;
+    if (mode == 0) {
+        if (t >= 2 * n_agg) return;
+    } else {
+        if (t >= n_agg) return;
+        t = 2 * t + (uint32_t)(mode - 1);
+    }
     uint32_t a = t >> 1;
     fp12 f;
     if (t & 1) {
@@ -241,6 +248,59 @@ __global__ void __launch_bounds__(64) k_g2_compress_aff(const uint32_t* __restri
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2_compress_affine(load_g2_aff(aff + 48 * (uint64_t)i), inf[i] != 0, out96 + 96 * (uint64_t)i);
+}
+
+// ------------------------------------------------------------------------------------------ committee shuffle
+// compute_shuffled_index (/root/reference/pos-evolution.md:513-534) for every index of the active set at once.
+// Stage 1: one thread per (round, 256-index block): source = SHA256(seed || round || LE32(block)); thread (round, 0) also
+// derives pivot = LE64(SHA256(seed || round)[0:8]) mod n.  Stage 2: one thread per index walks the rounds in order
+// (swap-or-not), reading one source bit per round from the 32 n/256-byte per-round table (L1/L2 resident).
+__global__ void __launch_bounds__(128) k_shuffle_sources(const uint8_t* __restrict__ seed32, uint32_t n, uint32_t rounds, uint32_t nblk,
+                                                          uint8_t* src, unsigned long long* pivots) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rounds * nblk) return;
+    uint32_t r = t / nblk, blk = t % nblk;
+    uint8_t buf[37];
+#pragma unroll 1
+    for (int i = 0; i < 32; i++) buf[i] = seed32[i];
+    buf[32] = (uint8_t)r;
+    buf[33] = (uint8_t)blk;
+    buf[34] = (uint8_t)(blk >> 8);
+    buf[35] = (uint8_t)(blk >> 16);
+    buf[36] = (uint8_t)(blk >> 24);
+    sha256_ctx c;
+    uint8_t out[32];
+    sha256_init(c);
+    sha256_update(c, buf, 37);
+    sha256_final(c, out);
+    uint8_t* dst = src + ((uint64_t)r * nblk + blk) * 32;
+#pragma unroll 1
+    for (int i = 0; i < 32; i++) dst[i] = out[i];
+    if (blk == 0) {
+        sha256_init(c);
+        sha256_update(c, buf, 33);
+        sha256_final(c, out);
+        unsigned long long v = 0;
+#pragma unroll
+        for (int i = 7; i >= 0; i--) v = (v << 8) | out[i];
+        pivots[r] = v % n;
+    }
+}
+// perm[i] = compute_shuffled_index(i); members_out[i] = active[perm[i]] (active == nullptr: identity)
+__global__ void __launch_bounds__(256) k_shuffle_apply(uint32_t n, uint32_t rounds, uint32_t nblk, const uint8_t* __restrict__ src,
+                                                        const unsigned long long* __restrict__ pivots, const uint32_t* __restrict__ active,
+                                                        uint32_t* members_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t idx = i;
+#pragma unroll 1
+    for (uint32_t r = 0; r < rounds; r++) {
+        uint64_t flip = (pivots[r] + n - idx) % n;
+        uint64_t pos = idx > flip ? idx : flip;
+        uint8_t byte = src[((uint64_t)r * nblk + (pos >> 8)) * 32 + ((pos & 255) >> 3)];
+        if ((byte >> (pos & 7)) & 1) idx = flip;
+    }
+    members_out[i] = active ? active[idx] : (uint32_t)idx;
 }
 
 // ------------------------------------------------------------------------------------------ K7: update_latest_messages

@@ -150,6 +150,15 @@ class Engine:
         self._ck(self.lib.b2_hash_to_g2(self.h, _p(msgs), msgs.shape[0], _p(out)))
         return out
 
+    def shuffle_committees(self, seed32: bytes, n_active: int, rounds: int, active=None):
+        """members[i] = active[compute_shuffled_index(i, n_active, seed)] for the whole active set, on the GPU."""
+        seed = np.frombuffer(bytes(seed32), dtype=np.uint8)
+        assert seed.shape == (32,)
+        act = _c(active, np.uint32) if active is not None else None
+        out = np.zeros(n_active, dtype=np.uint32)
+        self._ck(self.lib.b2_shuffle_committees(self.h, _p(seed), _p(act), n_active, rounds, _p(out)))
+        return out
+
     # ------------------------------------------------------------------ fork choice
     def latest_messages_reset(self):
         self._ck(self.lib.b2_latest_messages_reset(self.h))
@@ -213,6 +222,12 @@ class Engine:
         self._ck(self.lib.b2_latest_messages_update_dev(self.h, d_members.data_ptr(), d_off.data_ptr(), d_bits.data_ptr(), d_bits.shape[1],
                                                         d_target_epoch.data_ptr(), d_block_idx.data_ptr(),
                                                         d_accept.data_ptr() if d_accept is not None else None, n_agg, self._stream()))
+
+    def epoch_dev(self, d_sigs, d_members, d_off, d_bits, d_msgs, d_target_epoch, d_block_idx, d_agg_sig, d_agg_status, d_ok):
+        n_agg = d_off.numel() - 1
+        self._ck(self.lib.b2_epoch_dev(self.h, d_sigs.data_ptr(), d_members.data_ptr(), d_off.data_ptr(), d_bits.data_ptr(), d_bits.shape[1],
+                                       d_msgs.data_ptr(), d_target_epoch.data_ptr(), d_block_idx.data_ptr(), n_agg, d_sigs.numel() // 96,
+                                       d_agg_sig.data_ptr(), d_agg_status.data_ptr(), d_ok.data_ptr(), self._stream()))
 
     def vote_weights_dev(self, d_votes):
         self._ck(self.lib.b2_vote_weights_dev(self.h, d_votes.data_ptr(), self._stream()))

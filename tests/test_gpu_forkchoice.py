@@ -89,3 +89,14 @@ def test_latest_messages_update_order_exact(eng):
     assert np.array_equal(h, has_msg)
     assert np.array_equal(e[h == 1], msg_epoch[h == 1])
     assert np.array_equal(b[h == 1], msg_block[h == 1])
+
+
+@pytest.mark.parametrize("n,rounds", [(1, 10), (2, 10), (37, 10), (257, 90), (1000, 90), (1 << 20, 90)])
+def test_gpu_shuffle_matches_oracle(eng, n, rounds):
+    """compute_shuffled_index for the whole list on the GPU (SHA-256 + swap-or-not) vs the numpy oracle."""
+    import hashlib
+    seed = hashlib.sha256(b"shuffle" + n.to_bytes(4, "little")).digest()
+    ref = fast.shuffle_permutation(n, seed, rounds)
+    assert np.array_equal(eng.shuffle_committees(seed, n, rounds), ref)
+    active = (np.arange(n, dtype=np.uint32) * 3 + 7).astype(np.uint32)
+    assert np.array_equal(eng.shuffle_committees(seed, n, rounds, active), active[ref])
