@@ -19,6 +19,7 @@ struct dbuf {
 
 struct b2_ctx {
     int device = 0;
+    int n_sm = 148;
     cudaStream_t s_main = nullptr, s_aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     char err[512] = {0};
@@ -41,7 +42,7 @@ struct b2_ctx {
     uint32_t* d_head = nullptr;
     // scratch
     dbuf sc_pkjac, sc_pkst, sc_haff, sc_hflag, sc_saff, sc_sflag, sc_f, sc_g2aff, sc_g2st, sc_rec, sc_val;
-    dbuf in_a, in_b, in_c, in_d, in_e, in_f, in_g, out_a, out_b, sc_shuf, sc_pivot;
+    dbuf in_a, in_b, in_c, in_d, in_e, in_f, in_g, out_a, out_b, sc_shuf, sc_pivot, sc_sumjac;
 };
 
 static int fail_cuda(b2_ctx* c, cudaError_t e, const char* what) {
@@ -113,6 +114,8 @@ int b2_init(int device, b2_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_votes_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    ctx->n_sm = prop.multiProcessorCount;
     if (e != cudaSuccess) {
         delete ctx;
         return B2_ECUDA;
@@ -132,7 +135,7 @@ void b2_destroy(b2_ctx* ctx) {
         if (p) cudaFree(p);
     dbuf* bufs[] = {&ctx->sc_pkjac, &ctx->sc_pkst, &ctx->sc_haff, &ctx->sc_hflag, &ctx->sc_saff, &ctx->sc_sflag, &ctx->sc_f,
                     &ctx->sc_g2aff, &ctx->sc_g2st, &ctx->sc_rec, &ctx->sc_val, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d,
-                    &ctx->in_e, &ctx->in_f, &ctx->in_g, &ctx->out_a, &ctx->out_b, &ctx->sc_shuf, &ctx->sc_pivot};
+                    &ctx->in_e, &ctx->in_f, &ctx->in_g, &ctx->out_a, &ctx->out_b, &ctx->sc_shuf, &ctx->sc_pivot, &ctx->sc_sumjac};
     for (dbuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
@@ -248,20 +251,32 @@ int b2_g1_aggregate(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, c
 }
 
 // ------------------------------------------------------------------------------------------ bls.Aggregate
-int b2_aggregate_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig, uint8_t* d_out96,
-                     int32_t* d_seg_status, void* stream) {
-    REQUIRE(ctx && d_seg_off && d_out96 && d_seg_status && n_seg > 0 && (n_sig == 0 || d_sig96), "aggregate_dev: bad arguments");
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = (cudaStream_t)stream;
+// handoff: also leave the aggregate as an affine point + signature flag (subgroup-checked) in sc_saff / sc_sflag for verify_main
+static int aggregate_stages(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig, uint8_t* d_out96,
+                            int32_t* d_seg_status, bool handoff, cudaStream_t s) {
     int rc;
-    if ((rc = ensure(ctx, ctx->sc_g2aff, (size_t)n_sig * 192 + 16)) || (rc = ensure(ctx, ctx->sc_g2st, n_sig + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->sc_g2aff, (size_t)n_sig * 192 + 16)) || (rc = ensure(ctx, ctx->sc_g2st, n_sig + 16)) ||
+        (rc = ensure(ctx, ctx->sc_sumjac, (size_t)n_seg * 288)))
+        return rc;
+    if (handoff && ((rc = ensure(ctx, ctx->sc_saff, (size_t)n_seg * 192)) || (rc = ensure(ctx, ctx->sc_sflag, n_seg)))) return rc;
     if (n_sig) {
         k_g2_decompress<<<blocks_for(n_sig, 128), 128, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p);
         CKL(ctx);
     }
-    k_g2_segment_sum<<<n_seg, 128, 0, s>>>((const uint32_t*)ctx->sc_g2aff.p, (const uint8_t*)ctx->sc_g2st.p, d_seg_off, n_seg, d_out96, d_seg_status);
+    k_g2_segment_sum<<<n_seg, 128, 0, s>>>((const uint32_t*)ctx->sc_g2aff.p, (const uint8_t*)ctx->sc_g2st.p, d_seg_off, n_seg,
+                                           (uint32_t*)ctx->sc_sumjac.p, d_seg_status);
+    CKL(ctx);
+    k_g2_finish<<<blocks_for(n_seg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_sumjac.p, d_seg_status, n_seg, d_out96,
+                                                    handoff ? (uint32_t*)ctx->sc_saff.p : nullptr, handoff ? (uint8_t*)ctx->sc_sflag.p : nullptr);
     CKL(ctx);
     return B2_OK;
+}
+
+int b2_aggregate_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig, uint8_t* d_out96,
+                     int32_t* d_seg_status, void* stream) {
+    REQUIRE(ctx && d_seg_off && d_out96 && d_seg_status && n_seg > 0 && (n_sig == 0 || d_sig96), "aggregate_dev: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    return aggregate_stages(ctx, d_sig96, d_seg_off, n_seg, n_sig, d_out96, d_seg_status, false, (cudaStream_t)stream);
 }
 
 int b2_aggregate(b2_ctx* ctx, const uint8_t* sig96, const uint32_t* seg_off, uint32_t n_seg, uint8_t* out96, int32_t* seg_status) {
@@ -342,9 +357,12 @@ static int verify_fork(b2_ctx* ctx, const pk_source& P, const uint8_t* d_msg32, 
     CK(cudaEventRecord(ctx->ev_join[1], ctx->s_aux[1]));
     return B2_OK;
 }
+// d_sig96 == nullptr: the signature points are already in sc_saff / sc_sflag (handed over by aggregate_stages)
 static int verify_main(b2_ctx* ctx, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s) {
-    k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, s>>>(d_sig96, n_agg, (uint32_t*)ctx->sc_saff.p, (uint8_t*)ctx->sc_sflag.p);
-    CKL(ctx);
+    if (d_sig96) {
+        k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, s>>>(d_sig96, n_agg, (uint32_t*)ctx->sc_saff.p, (uint8_t*)ctx->sc_sflag.p);
+        CKL(ctx);
+    }
     k_miller<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_pkjac.p, (const uint8_t*)ctx->sc_pkst.p,
                                                   (const uint32_t*)ctx->sc_haff.p, (const uint8_t*)ctx->sc_hflag.p,
                                                   (const uint32_t*)ctx->sc_saff.p, (const uint8_t*)ctx->sc_sflag.p, n_agg,
@@ -383,8 +401,8 @@ int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members,
     int rc;
     pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
     if ((rc = verify_fork(ctx, P, d_msg32, n_agg, s))) return rc;
-    if ((rc = b2_aggregate_dev(ctx, d_sig96, d_off, n_agg, n_sig, d_agg_sig96, d_agg_status, s))) return rc;
-    if ((rc = verify_main(ctx, d_agg_sig96, n_agg, d_ok_out, s))) return rc;
+    if ((rc = aggregate_stages(ctx, d_sig96, d_off, n_agg, n_sig, d_agg_sig96, d_agg_status, true, s))) return rc;
+    if ((rc = verify_main(ctx, nullptr, n_agg, d_ok_out, s))) return rc;
     return b2_latest_messages_update_dev(ctx, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_ok_out, n_agg, s);
 }
 
@@ -674,8 +692,14 @@ int b2_vote_weights_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, void* stream) {
     REQUIRE(ctx->n_val > 0 && ctx->n_blocks > 0, "vote_weights: registry or tree not loaded");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
-    k_ghost_votes<<<blocks_for(ctx->n_val, 256), 256, 0, s>>>(ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff,
+    const size_t bins_bytes = (size_t)ctx->n_blocks * 8;
+    if (bins_bytes <= 200 * 1024) {
+        k_ghost_votes_smem<<<ctx->n_sm, 1024, bins_bytes, s>>>(ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff,
                                                               ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder);
+    } else {
+        k_ghost_votes<<<blocks_for(ctx->n_val, 256), 256, 0, s>>>(ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff,
+                                                                  ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder);
+    }
     CKL(ctx);
     return B2_OK;
 }

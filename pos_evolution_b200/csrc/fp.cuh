@@ -173,39 +173,35 @@ HD fp fp_mul3(const fp& a) { return fp_add(fp_dbl(a), a); }
 HD fp fp_mul4(const fp& a) { return fp_dbl(fp_dbl(a)); }
 HD fp fp_mul8(const fp& a) { return fp_dbl(fp_mul4(a)); }
 
-// a^e for a 384-bit exponent stored canonically in the constant table at `off` (uniform across
-// threads, so the bit tests do not diverge).  Fixed 4-bit window, 96 windows.
-HDN fp fp_pow_const(const fp& a, int off) {
-    fp tbl[16];
-    tbl[0] = fp_one();
-    tbl[1] = a;
+// a^e for a fixed exponent given as a sliding-window schedule in the constant table (tools/gen_consts.py:
+// word 0 = number of steps, then (n_squarings << 8 | table index), index 255 = squarings only; window 4, table of the
+// eight odd powers a^1..a^15).  The schedule is the same in every thread, so nothing diverges.  For (p-3)/4 this is
+// 379 squarings + 76 multiplications + 8 for the table (the fixed-window version needed 380 + 92 + 14).
+HDN fp fp_pow_prog(const fp& a, int off) {
+    const uint32_t* prog = const_table() + off;
+    fp tbl[8];
+    fp a2 = fp_mul(a, a);
+    tbl[0] = a;
 #pragma unroll 1
-    for (int i = 2; i < 16; i++) tbl[i] = fp_mul(tbl[i - 1], a);
-    const uint32_t* e = const_table() + off;
-    fp r = fp_one();
-    bool started = false;
+    for (int i = 1; i < 8; i++) tbl[i] = fp_mul(tbl[i - 1], a2);
+    const uint32_t n = prog[0];
+    fp r = tbl[prog[1] & 0xffu];
 #pragma unroll 1
-    for (int w = 95; w >= 0; w--) {
-        uint32_t nib = (e[w >> 3] >> ((w & 7) * 4)) & 15u;
-        if (started) {
-            r = fp_sqr(r);
-            r = fp_sqr(r);
-            r = fp_sqr(r);
-            r = fp_sqr(r);
-        }
-        if (nib) {
-            r = started ? fp_mul(r, tbl[nib]) : tbl[nib];
-            started = true;
-        }
+    for (uint32_t k = 2; k <= n; k++) {
+        const uint32_t op = prog[k];
+#pragma unroll 1
+        for (uint32_t s = op >> 8; s; s--) r = fp_mul(r, r);
+        const uint32_t idx = op & 0xffu;
+        if (idx != 0xffu) r = fp_mul(r, tbl[idx]);
     }
     return r;
 }
 
-HD fp fp_inv(const fp& a) { return fp_pow_const(a, C_EXP_PM2); }        // 0 -> 0
+HD fp fp_inv(const fp& a) { return fp_pow_prog(a, C_PROG_PM2); }        // 0 -> 0
 
 // d = a^((p-3)/4).  Then a*d = a^((p+1)/4) is the square-root candidate and, when a is a
 // non-zero square, d = 1/sqrt(a).
-HD fp fp_pow_pm3d4(const fp& a) { return fp_pow_const(a, C_EXP_PM3D4); }
+HD fp fp_pow_pm3d4(const fp& a) { return fp_pow_prog(a, C_PROG_PM3D4); }
 
 // sqrt in Fp: returns true and writes a root when `a` is a square
 HD bool fp_sqrt(const fp& a, fp& root) {

@@ -115,10 +115,11 @@ __global__ void __launch_bounds__(128) k_g2_decompress(const uint8_t* __restrict
     for (int k = 0; k < 12; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
     st_out[i] = (uint8_t)st;
 }
-// stage 2: one block per segment: mixed additions + tree, compress
-__global__ void __launch_bounds__(128) k_g2_segment_sum(const uint32_t* __restrict__ aff, const uint8_t* __restrict__ st,
-                                                         const uint32_t* __restrict__ seg_off, uint32_t n_seg, uint8_t* out96,
-                                                         int32_t* seg_status) {
+// stage 2: one block per segment: mixed additions + tree -> Jacobian sum (72 words) + status.  The inversion needed for
+// the compressed encoding is NOT done here (127 threads would idle behind it): stage 3 does it with a thread per segment.
+__global__ void __launch_bounds__(128, 3) k_g2_segment_sum(const uint32_t* __restrict__ aff, const uint8_t* __restrict__ st,
+                                                            const uint32_t* __restrict__ seg_off, uint32_t n_seg, uint32_t* sum_jac,
+                                                            int32_t* seg_status) {
     __shared__ g2_jac red[4];
     const uint32_t s = blockIdx.x;
     if (s >= n_seg) return;
@@ -144,7 +145,47 @@ __global__ void __launch_bounds__(128) k_g2_segment_sum(const uint32_t* __restri
     }
     acc = block_sum_points(acc, red);
     bad = __syncthreads_or((int)bad);
-    if (threadIdx.x == 0) core_g2_agg_finish(acc, bad, end - begin, s, out96, seg_status);
+    if (threadIdx.x == 0) {
+        seg_status[s] = bad ? 1 : (end == begin ? 2 : 0);
+        uint32_t* o = sum_jac + 72 * (uint64_t)s;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&acc);
+#pragma unroll 1
+        for (int k = 0; k < 72; k++) o[k] = w[k];
+    }
+}
+// stage 3: one thread per segment: Jacobian sum -> affine (one Fp2 inversion) -> compressed 96 bytes (bls.Aggregate's result).
+// When `s_aff` is given (epoch pipeline) the affine point and its signature flag are handed to the verification stage
+// directly -- compress followed by decompress is the identity, so the Fp2 square root of the aggregate is skipped -- and
+// the G2 subgroup check FastAggregateVerify performs on the signature is done here.
+__global__ void __launch_bounds__(32) k_g2_finish(const uint32_t* __restrict__ sum_jac, const int32_t* __restrict__ seg_status, uint32_t n_seg,
+                                                   uint8_t* out96, uint32_t* s_aff, uint8_t* sflag) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    g2_jac acc;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&acc);
+    const uint32_t* in = sum_jac + 72 * (uint64_t)s;
+#pragma unroll 1
+    for (int k = 0; k < 72; k++) w[k] = in[k];
+    const int32_t st = seg_status[s];
+    g2_aff a;
+    a.x = fp2_zero();
+    a.y = fp2_zero();
+    bool finite = (st == 0) && pt_to_affine(acc, a);
+    uint8_t* o = out96 + 96 * (uint64_t)s;
+    if (st != 0) {
+#pragma unroll 1
+        for (int k = 0; k < 96; k++) o[k] = 0;
+    } else {
+        g2_compress_affine(a, !finite, o);
+    }
+    if (s_aff) {
+        uint8_t f = (st != 0) ? SIG_INVALID : (!finite ? SIG_INFINITY : (g2_in_subgroup(pt_from_affine(a)) ? SIG_OK : SIG_INVALID));
+        uint32_t* oa = s_aff + 48 * (uint64_t)s;
+        const uint32_t* wa = reinterpret_cast<const uint32_t*>(&a);
+#pragma unroll 1
+        for (int k = 0; k < 48; k++) oa[k] = wa[k];
+        sflag[s] = f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ K4-K6: verification pipeline
@@ -374,6 +415,52 @@ __global__ void __launch_bounds__(256) k_ghost_votes(uint64_t n, const unsigned 
         if ((peers >> l) & 1u) sum += o;
     }
     if (on && lane == __ffs(peers) - 1) atomicAdd(&votes[b], sum);
+}
+
+// Same scatter with the per-block bins privatised in shared memory (used when n_blocks * 8 B fits): a persistent grid
+// of one CTA per SM strides over the validators; lanes of a warp voting for the same block are combined first, the
+// leader adds into the CTA's shared bins, and only non-zero bins are flushed to global memory -- one atomic per
+// (CTA, voted block) instead of one per (warp, voted block), which matters when a million validators agree on a
+// handful of recent blocks (the realistic case) and the global atomics would serialise on those addresses.
+__global__ void __launch_bounds__(1024) k_ghost_votes_smem(uint64_t n, const unsigned long long* __restrict__ lmd_key,
+                                                            const uint32_t* __restrict__ lmd_block, const uint8_t* __restrict__ equiv,
+                                                            const uint8_t* __restrict__ flags, const uint64_t* __restrict__ eff,
+                                                            const uint32_t* __restrict__ pre, uint32_t n_blocks, unsigned long long* votes) {
+    extern __shared__ unsigned long long bins[];
+    for (uint32_t i = threadIdx.x; i < n_blocks; i += blockDim.x) bins[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + stride - 1) / stride * stride;            // whole warps stay converged for the shuffles
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_round; v += stride) {
+        bool on = v < n;
+        uint32_t b = 0xffffffffu;
+        unsigned long long bal = 0;
+        if (on) {
+            on = lmd_key[v] != 0 && !equiv[v] && (flags[v] & 1);
+            if (on) {
+                uint32_t blk = lmd_block[v];
+                on = blk < n_blocks;
+                if (on) {
+                    b = pre[blk];
+                    bal = eff[v];
+                }
+            }
+        }
+        unsigned peers = __match_any_sync(B2_FULL_MASK, b);
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int l = 0; l < 32; l++) {
+            unsigned long long o = __shfl_sync(B2_FULL_MASK, bal, l);
+            if ((peers >> l) & 1u) sum += o;
+        }
+        if (on && lane == __ffs(peers) - 1) atomicAdd(&bins[b], sum);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_blocks; i += blockDim.x) {
+        unsigned long long w = bins[i];
+        if (w) atomicAdd(&votes[i], w);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ K9: subtree weights + head

@@ -73,6 +73,38 @@ ISO_YNUM = [
 ISO_YDEN = [(P - 432, P - 432), (0, P - 216), (18, P - 18)]  # + monic x^3
 
 
+def sliding_window_program(e, w=4):
+    """Constant-exponent sliding-window schedule: list of (n_squarings, table_index) with table[k] = a^(2k+1);
+    index 255 = squarings only.  First entry's squarings are 0 (the accumulator is initialised from the table)."""
+    bits = bin(e)[2:]
+    ops, i, pending, first = [], 0, 0, True
+    n = len(bits)
+    while i < n:
+        if bits[i] == "0":
+            pending += 1
+            i += 1
+            continue
+        j = min(n, i + w)
+        while bits[j - 1] == "0":
+            j -= 1
+        val = int(bits[i:j], 2)
+        ops.append((0 if first else pending + (j - i), (val - 1) // 2))
+        first, pending, i = False, 0, j
+    if pending:
+        ops.append((pending, 255))
+    # self-check against pow()
+    a = 0x1234567
+    tbl = [pow(a, 2 * k + 1, P) for k in range(1 << (w - 1))]
+    r = tbl[ops[0][1]]
+    for nsq, idx in ops[1:]:
+        for _ in range(nsq):
+            r = r * r % P
+        if idx != 255:
+            r = r * tbl[idx] % P
+    assert r == pow(a, e, P)
+    return ops
+
+
 def build():
     """-> ordered list of (name, kind, value); kind in {'fp','fp2','raw'}; raw = not Montgomery."""
     c = []
@@ -86,6 +118,9 @@ def build():
     raw("C_EXP_PM3D4", (P - 3) // 4)                        # a^((p-3)/4): inverse-sqrt / sqrt building block
     raw("C_EXP_PM2", P - 2)                                 # Fermat inverse
     raw("C_R_ORDER", R_ORDER)                               # subgroup order, 255 bits (top limbs zero)
+    for name, e in (("C_PROG_PM3D4", (P - 3) // 4), ("C_PROG_PM2", P - 2)):
+        ops = sliding_window_program(e, 4)
+        c.append((name, "words", [len(ops)] + [(nsq << 8) | idx for nsq, idx in ops]))
     fp("C_ONE", 1)
     fp("C_TWO_INV", pow(2, -1, P))
     fp("C_TWO256", 1 << 256)                                # hash_to_field: (hi*2^256 + lo) mod p
@@ -140,7 +175,9 @@ def table():
     words, offsets = [], []
     for name, kind, v in build():
         offsets.append((name, len(words)))
-        if kind == "raw":
+        if kind == "words":
+            words += list(v)
+        elif kind == "raw":
             words += limbs(v)
         elif kind == "fp":
             words += limbs(mont(v))
