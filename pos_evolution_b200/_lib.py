@@ -51,6 +51,9 @@ SIGNATURES = {
     "b2_latest_messages_update_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
     "b2_epoch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_uint64,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2_epoch_start_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_uint32, c_uint64, c_void_p, c_void_p]),
+    "b2_epoch_tail_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "b2_epoch_wait_dev": (c_int, [c_void_p, c_int, c_void_p]),
     "b2_vote_weights_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b2_head_from_votes_dev": (c_int, [c_void_p, c_void_p, c_uint32, c_int32, c_uint64, c_void_p, c_void_p, c_void_p]),
     "b2_tree_size": (c_uint32, [c_void_p]),

@@ -17,11 +17,17 @@ struct dbuf {
     size_t cap = 0;
 };
 
+struct vslot {
+    dbuf haff, hflag, pkjac, pkst, saff, sflag, f, sumjac;
+    cudaEvent_t ev_join0 = nullptr, ev_join1 = nullptr, ev_seg = nullptr, ev_tail_done = nullptr;
+};
+
 struct b2_ctx {
     int device = 0;
     int n_sm = 148;
-    cudaStream_t s_main = nullptr, s_aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaStream_t s_main = nullptr, s_aux[2] = {nullptr, nullptr}, s_tail = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_votes_done = nullptr;
+    vslot slot[2];
     char err[512] = {0};
     uint64_t launches = 0;
     // registry
@@ -41,8 +47,8 @@ struct b2_ctx {
     unsigned long long *d_votes = nullptr, *d_prefix = nullptr, *d_weight = nullptr;
     uint32_t* d_head = nullptr;
     // scratch
-    dbuf sc_pkjac, sc_pkst, sc_haff, sc_hflag, sc_saff, sc_sflag, sc_f, sc_g2aff, sc_g2st, sc_rec, sc_val;
-    dbuf in_a, in_b, in_c, in_d, in_e, in_f, in_g, out_a, out_b, sc_shuf, sc_pivot, sc_sumjac;
+    dbuf sc_pkjac, sc_pkst, sc_haff, sc_hflag, sc_g2aff, sc_g2st, sc_rec, sc_val;
+    dbuf in_a, in_b, in_c, in_d, in_e, in_f, in_g, out_a, out_b, sc_shuf, sc_pivot;
 };
 
 static int fail_cuda(b2_ctx* c, cudaError_t e, const char* what) {
@@ -111,8 +117,13 @@ int b2_init(int device, b2_ctx** out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaError_t e = cudaStreamCreateWithPriority(&ctx->s_main, cudaStreamNonBlocking, prio_lo);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithPriority(&ctx->s_aux[i], cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->s_tail, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_votes_done, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        cudaEvent_t* evs[4] = {&ctx->slot[i].ev_join0, &ctx->slot[i].ev_join1, &ctx->slot[i].ev_seg, &ctx->slot[i].ev_tail_done};
+        for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(evs[k], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_votes_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     ctx->n_sm = prop.multiProcessorCount;
@@ -133,16 +144,24 @@ void b2_destroy(b2_ctx* ctx) {
                     ctx->d_weight, ctx->d_head};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    dbuf* bufs[] = {&ctx->sc_pkjac, &ctx->sc_pkst, &ctx->sc_haff, &ctx->sc_hflag, &ctx->sc_saff, &ctx->sc_sflag, &ctx->sc_f,
+    dbuf* bufs[] = {&ctx->sc_pkjac, &ctx->sc_pkst, &ctx->sc_haff, &ctx->sc_hflag,
                     &ctx->sc_g2aff, &ctx->sc_g2st, &ctx->sc_rec, &ctx->sc_val, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d,
-                    &ctx->in_e, &ctx->in_f, &ctx->in_g, &ctx->out_a, &ctx->out_b, &ctx->sc_shuf, &ctx->sc_pivot, &ctx->sc_sumjac};
+                    &ctx->in_e, &ctx->in_f, &ctx->in_g, &ctx->out_a, &ctx->out_b, &ctx->sc_shuf, &ctx->sc_pivot};
     for (dbuf* b : bufs)
         if (b->p) cudaFree(b->p);
-    if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     for (int i = 0; i < 2; i++) {
+        vslot& V = ctx->slot[i];
+        dbuf* vb[] = {&V.haff, &V.hflag, &V.pkjac, &V.pkst, &V.saff, &V.sflag, &V.f, &V.sumjac};
+        for (dbuf* b : vb)
+            if (b->p) cudaFree(b->p);
+        cudaEvent_t evs[4] = {V.ev_join0, V.ev_join1, V.ev_seg, V.ev_tail_done};
+        for (cudaEvent_t ev : evs)
+            if (ev) cudaEventDestroy(ev);
         if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
-        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
+    if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    if (ctx->s_tail) cudaStreamDestroy(ctx->s_tail);
+    if (ctx->ev_votes_done) cudaEventDestroy(ctx->ev_votes_done);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
@@ -251,23 +270,28 @@ int b2_g1_aggregate(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, c
 }
 
 // ------------------------------------------------------------------------------------------ bls.Aggregate
-// handoff: also leave the aggregate as an affine point + signature flag (subgroup-checked) in sc_saff / sc_sflag for verify_main
-static int aggregate_stages(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig, uint8_t* d_out96,
-                            int32_t* d_seg_status, bool handoff, cudaStream_t s) {
+// front: stage 1 + 2 (decompress every signature, per-segment Jacobian sums into V.sumjac);  finish: stage 3 (one
+// inversion per segment -> compressed bytes; with `handoff` also the affine point + subgroup-checked flag for verify_main).
+static int aggregate_front(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig,
+                           int32_t* d_seg_status, cudaStream_t s) {
     int rc;
     if ((rc = ensure(ctx, ctx->sc_g2aff, (size_t)n_sig * 192 + 16)) || (rc = ensure(ctx, ctx->sc_g2st, n_sig + 16)) ||
-        (rc = ensure(ctx, ctx->sc_sumjac, (size_t)n_seg * 288)))
+        (rc = ensure(ctx, V.sumjac, (size_t)n_seg * 288)))
         return rc;
-    if (handoff && ((rc = ensure(ctx, ctx->sc_saff, (size_t)n_seg * 192)) || (rc = ensure(ctx, ctx->sc_sflag, n_seg)))) return rc;
     if (n_sig) {
         k_g2_decompress<<<blocks_for(n_sig, 128), 128, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p);
         CKL(ctx);
     }
     k_g2_segment_sum<<<n_seg, 128, 0, s>>>((const uint32_t*)ctx->sc_g2aff.p, (const uint8_t*)ctx->sc_g2st.p, d_seg_off, n_seg,
-                                           (uint32_t*)ctx->sc_sumjac.p, d_seg_status);
+                                           (uint32_t*)V.sumjac.p, d_seg_status);
     CKL(ctx);
-    k_g2_finish<<<blocks_for(n_seg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_sumjac.p, d_seg_status, n_seg, d_out96,
-                                                    handoff ? (uint32_t*)ctx->sc_saff.p : nullptr, handoff ? (uint8_t*)ctx->sc_sflag.p : nullptr);
+    return B2_OK;
+}
+static int aggregate_finish(b2_ctx* ctx, vslot& V, uint32_t n_seg, uint8_t* d_out96, const int32_t* d_seg_status, bool handoff, cudaStream_t s) {
+    int rc;
+    if (handoff && ((rc = ensure(ctx, V.saff, (size_t)n_seg * 192)) || (rc = ensure(ctx, V.sflag, n_seg)))) return rc;
+    k_g2_finish<<<blocks_for(n_seg, 32), 32, 0, s>>>((const uint32_t*)V.sumjac.p, d_seg_status, n_seg, d_out96,
+                                                    handoff ? (uint32_t*)V.saff.p : nullptr, handoff ? (uint8_t*)V.sflag.p : nullptr);
     CKL(ctx);
     return B2_OK;
 }
@@ -276,7 +300,9 @@ int b2_aggregate_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_
                      int32_t* d_seg_status, void* stream) {
     REQUIRE(ctx && d_seg_off && d_out96 && d_seg_status && n_seg > 0 && (n_sig == 0 || d_sig96), "aggregate_dev: bad arguments");
     CK(cudaSetDevice(ctx->device));
-    return aggregate_stages(ctx, d_sig96, d_seg_off, n_seg, n_sig, d_out96, d_seg_status, false, (cudaStream_t)stream);
+    int rc;
+    if ((rc = aggregate_front(ctx, ctx->slot[0], d_sig96, d_seg_off, n_seg, n_sig, d_seg_status, (cudaStream_t)stream))) return rc;
+    return aggregate_finish(ctx, ctx->slot[0], n_seg, d_out96, d_seg_status, false, (cudaStream_t)stream);
 }
 
 int b2_aggregate(b2_ctx* ctx, const uint8_t* sig96, const uint32_t* seg_off, uint32_t n_seg, uint8_t* out96, int32_t* seg_status) {
@@ -312,8 +338,8 @@ int b2_aggregate(b2_ctx* ctx, const uint8_t* sig96, const uint32_t* seg_off, uin
 //   aux1: K2 pubkey gather+aggregate (or the explicit-key variant), then [after aux0] the Miller loop e(PK_agg, H(m))
 //   main: signature decompression + subgroup check, Miller loop e(-g1, sig), [join aux1] final exponentiation.
 // verify_fork() enqueues the side work forked from the *current* position of the caller's stream, verify_main()
-// the signature half; b2_epoch_dev calls verify_fork() BEFORE it enqueues the epoch's signature aggregation so that
-// the side work overlaps with it.
+// the signature half.  All intermediate buffers and events live in a `vslot`; the pipelined epoch API alternates
+// between two slots so that the latency-bound tail of epoch k overlaps with the signature decompression of epoch k+1.
 struct pk_source {
     const uint32_t *d_members, *d_off;
     const uint8_t* d_bits;
@@ -321,56 +347,52 @@ struct pk_source {
     const uint8_t* d_pk48;      // explicit-key form when non-null (d_off = pk offsets)
     uint64_t n_pk;
 };
-static int verify_fork(b2_ctx* ctx, const pk_source& P, const uint8_t* d_msg32, uint32_t n_agg, cudaStream_t s) {
+static int verify_fork(b2_ctx* ctx, vslot& V, const pk_source& P, const uint8_t* d_msg32, uint32_t n_agg, cudaStream_t s) {
     int rc;
-    if ((rc = ensure(ctx, ctx->sc_haff, (size_t)n_agg * 192)) || (rc = ensure(ctx, ctx->sc_hflag, n_agg)) ||
-        (rc = ensure(ctx, ctx->sc_saff, (size_t)n_agg * 192)) || (rc = ensure(ctx, ctx->sc_sflag, n_agg)) ||
-        (rc = ensure(ctx, ctx->sc_f, (size_t)n_agg * 2 * 576)) || (rc = ensure(ctx, ctx->sc_pkjac, (size_t)n_agg * 144)) ||
-        (rc = ensure(ctx, ctx->sc_pkst, n_agg)))
+    if ((rc = ensure(ctx, V.haff, (size_t)n_agg * 192)) || (rc = ensure(ctx, V.hflag, n_agg)) || (rc = ensure(ctx, V.saff, (size_t)n_agg * 192)) ||
+        (rc = ensure(ctx, V.sflag, n_agg)) || (rc = ensure(ctx, V.f, (size_t)n_agg * 2 * 576)) || (rc = ensure(ctx, V.pkjac, (size_t)n_agg * 144)) ||
+        (rc = ensure(ctx, V.pkst, n_agg)))
         return rc;
     if (P.d_pk48 && ((rc = ensure(ctx, ctx->sc_rec, P.n_pk * 96 + 16)) || (rc = ensure(ctx, ctx->sc_val, P.n_pk + 16)))) return rc;
     CK(cudaEventRecord(ctx->ev_fork, s));
     CK(cudaStreamWaitEvent(ctx->s_aux[0], ctx->ev_fork, 0));
     CK(cudaStreamWaitEvent(ctx->s_aux[1], ctx->ev_fork, 0));
-    k_hash_to_g2<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->sc_hflag.p);
+    k_hash_to_g2<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)V.haff.p, (uint8_t*)V.hflag.p);
     CKL(ctx);
-    CK(cudaEventRecord(ctx->ev_join[0], ctx->s_aux[0]));
+    CK(cudaEventRecord(V.ev_join0, ctx->s_aux[0]));
     if (P.d_pk48) {
         if (P.n_pk) {
             k_g1_decompress_validate<<<blocks_for(P.n_pk, 128), 128, 0, ctx->s_aux[1]>>>(P.d_pk48, P.n_pk, (uint32_t*)ctx->sc_rec.p, (uint8_t*)ctx->sc_val.p);
             CKL(ctx);
         }
         k_g1_segment_sum<<<n_agg, 128, 0, ctx->s_aux[1]>>>((const uint32_t*)ctx->sc_rec.p, (const uint8_t*)ctx->sc_val.p, P.d_off, n_agg,
-                                                          (uint32_t*)ctx->sc_pkjac.p, (uint8_t*)ctx->sc_pkst.p);
+                                                          (uint32_t*)V.pkjac.p, (uint8_t*)V.pkst.p);
         CKL(ctx);
     } else {
         k_g1_aggregate<<<n_agg, 128, 0, ctx->s_aux[1]>>>(ctx->d_records, ctx->d_valid, P.d_members, P.d_off, P.d_bits, P.bits_stride, n_agg,
-                                                        (uint32_t*)ctx->sc_pkjac.p, (uint8_t*)ctx->sc_pkst.p);
+                                                        (uint32_t*)V.pkjac.p, (uint8_t*)V.pkst.p);
         CKL(ctx);
     }
-    CK(cudaStreamWaitEvent(ctx->s_aux[1], ctx->ev_join[0], 0));
-    k_miller<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[1]>>>((const uint32_t*)ctx->sc_pkjac.p, (const uint8_t*)ctx->sc_pkst.p,
-                                                             (const uint32_t*)ctx->sc_haff.p, (const uint8_t*)ctx->sc_hflag.p,
-                                                             (const uint32_t*)ctx->sc_saff.p, (const uint8_t*)ctx->sc_sflag.p, n_agg,
-                                                             (uint32_t*)ctx->sc_f.p, 1);
+    CK(cudaStreamWaitEvent(ctx->s_aux[1], V.ev_join0, 0));
+    k_miller<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[1]>>>((const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p,
+                                                             (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p, (const uint8_t*)V.sflag.p, n_agg,
+                                                             (uint32_t*)V.f.p, 1);
     CKL(ctx);
-    CK(cudaEventRecord(ctx->ev_join[1], ctx->s_aux[1]));
+    CK(cudaEventRecord(V.ev_join1, ctx->s_aux[1]));
     return B2_OK;
 }
-// d_sig96 == nullptr: the signature points are already in sc_saff / sc_sflag (handed over by aggregate_stages)
-static int verify_main(b2_ctx* ctx, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s) {
+// d_sig96 == nullptr: the signature points are already in V.saff / V.sflag (handed over by aggregate_finish)
+static int verify_main(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s) {
     if (d_sig96) {
-        k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, s>>>(d_sig96, n_agg, (uint32_t*)ctx->sc_saff.p, (uint8_t*)ctx->sc_sflag.p);
+        k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, s>>>(d_sig96, n_agg, (uint32_t*)V.saff.p, (uint8_t*)V.sflag.p);
         CKL(ctx);
     }
-    k_miller<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_pkjac.p, (const uint8_t*)ctx->sc_pkst.p,
-                                                  (const uint32_t*)ctx->sc_haff.p, (const uint8_t*)ctx->sc_hflag.p,
-                                                  (const uint32_t*)ctx->sc_saff.p, (const uint8_t*)ctx->sc_sflag.p, n_agg,
-                                                  (uint32_t*)ctx->sc_f.p, 2);
+    k_miller<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p,
+                                                  (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p, (const uint8_t*)V.sflag.p, n_agg,
+                                                  (uint32_t*)V.f.p, 2);
     CKL(ctx);
-    CK(cudaStreamWaitEvent(s, ctx->ev_join[1], 0));
-    k_final_verdict<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)ctx->sc_f.p, (const uint8_t*)ctx->sc_pkst.p,
-                                                        (const uint8_t*)ctx->sc_sflag.p, n_agg, d_ok);
+    CK(cudaStreamWaitEvent(s, V.ev_join1, 0));
+    k_final_verdict<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)V.f.p, (const uint8_t*)V.pkst.p, (const uint8_t*)V.sflag.p, n_agg, d_ok);
     CKL(ctx);
     return B2_OK;
 }
@@ -383,13 +405,42 @@ int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const u
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
-    if ((rc = verify_fork(ctx, P, d_msg32, n_agg, s))) return rc;
-    return verify_main(ctx, d_sig96, n_agg, d_ok_out, s);
+    if ((rc = verify_fork(ctx, ctx->slot[0], P, d_msg32, n_agg, s))) return rc;
+    return verify_main(ctx, ctx->slot[0], d_sig96, n_agg, d_ok_out, s);
 }
 
-// One epoch for the validators of this rank: per-committee bls.Aggregate of the individual signatures, FastAggregateVerify
-// of the aggregates, update_latest_messages for the accepted ones.  The signature-independent half of the verification
-// is forked first so it overlaps with the (grid-filling) signature decompression.
+// ---- one epoch for the validators of this rank: per-committee bls.Aggregate of the individual signatures,
+// FastAggregateVerify of the aggregates, update_latest_messages for the accepted ones.
+//   epoch_start: fork the signature-independent half (hash, pubkey aggregation, first Miller loop) on the side streams,
+//                then decompress + segment-sum the signatures on the caller's stream (the grid-filling part);
+//   epoch_tail : inversion/compress + subgroup check, second Miller loop, final exponentiation, LMD update -- latency-
+//                bound work on few SMs; on `tail_stream` (the caller's own stream, or the context's tail stream so that
+//                it overlaps with the next epoch's epoch_start in the other slot).
+static int epoch_start(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
+                       uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, cudaStream_t s) {
+    vslot& V = ctx->slot[slot];
+    int rc;
+    CK(cudaStreamWaitEvent(s, V.ev_tail_done, 0));      // the slot's previous user (two epochs ago) must have drained
+    pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
+    if ((rc = verify_fork(ctx, V, P, d_msg32, n_agg, s))) return rc;
+    if ((rc = aggregate_front(ctx, V, d_sig96, d_off, n_agg, n_sig, d_agg_status, s))) return rc;
+    CK(cudaEventRecord(V.ev_seg, s));
+    return B2_OK;
+}
+static int epoch_tail(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
+                      const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
+                      uint8_t* d_ok_out, cudaStream_t t) {
+    vslot& V = ctx->slot[slot];
+    int rc;
+    CK(cudaStreamWaitEvent(t, V.ev_seg, 0));
+    if ((rc = aggregate_finish(ctx, V, n_agg, d_agg_sig96, d_agg_status, true, t))) return rc;
+    if ((rc = verify_main(ctx, V, nullptr, n_agg, d_ok_out, t))) return rc;
+    CK(cudaStreamWaitEvent(t, ctx->ev_votes_done, 0));  // do not move the LMD table under a vote scatter that is still reading it
+    if ((rc = b2_latest_messages_update_dev(ctx, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_ok_out, n_agg, t))) return rc;
+    CK(cudaEventRecord(V.ev_tail_done, t));
+    return B2_OK;
+}
+
 int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                  uint32_t bits_stride, const uint8_t* d_msg32, const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg,
                  uint64_t n_sig, uint8_t* d_agg_sig96, int32_t* d_agg_status, uint8_t* d_ok_out, void* stream) {
@@ -399,11 +450,34 @@ int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members,
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
-    if ((rc = verify_fork(ctx, P, d_msg32, n_agg, s))) return rc;
-    if ((rc = aggregate_stages(ctx, d_sig96, d_off, n_agg, n_sig, d_agg_sig96, d_agg_status, true, s))) return rc;
-    if ((rc = verify_main(ctx, nullptr, n_agg, d_ok_out, s))) return rc;
-    return b2_latest_messages_update_dev(ctx, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_ok_out, n_agg, s);
+    if ((rc = epoch_start(ctx, 0, d_sig96, d_members, d_off, d_bits, bits_stride, d_msg32, n_agg, n_sig, d_agg_status, s))) return rc;
+    return epoch_tail(ctx, 0, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, n_agg, d_agg_sig96, d_agg_status, d_ok_out, s);
+}
+
+// Pipelined form: call start(slot), then [finish the previous epoch: b2_epoch_wait_dev(other slot) + vote weights + head], then
+// tail(slot); alternate slot = 0, 1, 0, ...  The tail runs on the context's own high-priority stream.
+int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
+                       uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, void* stream) {
+    REQUIRE(ctx && (slot == 0 || slot == 1) && d_sig96 && d_members && d_off && d_bits && d_msg32 && d_agg_status && n_agg > 0 && bits_stride > 0,
+            "epoch_start_dev: bad arguments");
+    REQUIRE(ctx->n_val > 0, "epoch_start_dev: registry not loaded");
+    CK(cudaSetDevice(ctx->device));
+    return epoch_start(ctx, slot, d_sig96, d_members, d_off, d_bits, bits_stride, d_msg32, n_agg, n_sig, d_agg_status, (cudaStream_t)stream);
+}
+int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
+                      const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
+                      uint8_t* d_ok_out) {
+    REQUIRE(ctx && (slot == 0 || slot == 1) && d_members && d_off && d_bits && d_target_epoch && d_block_idx && d_agg_sig96 && d_agg_status && d_ok_out &&
+                n_agg > 0 && bits_stride > 0, "epoch_tail_dev: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    return epoch_tail(ctx, slot, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, n_agg, d_agg_sig96, d_agg_status, d_ok_out,
+                      ctx->s_tail);
+}
+int b2_epoch_wait_dev(b2_ctx* ctx, int slot, void* stream) {
+    REQUIRE(ctx && (slot == 0 || slot == 1), "epoch_wait_dev: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->slot[slot].ev_tail_done, 0));
+    return B2_OK;
 }
 
 int b2_fast_aggregate_verify(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
@@ -449,8 +523,8 @@ int b2_fast_aggregate_verify_pks(b2_ctx* ctx, const uint8_t* pk48, const uint32_
     CK(cudaMemcpyAsync(ctx->in_d.p, sig96, (size_t)n_agg * 96, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->in_e.p, msg32, (size_t)n_agg * 32, cudaMemcpyHostToDevice, s));
     pk_source P = {nullptr, (const uint32_t*)ctx->in_b.p, nullptr, 0, (const uint8_t*)ctx->in_a.p, n_pk};
-    if ((rc = verify_fork(ctx, P, (const uint8_t*)ctx->in_e.p, n_agg, s))) return rc;
-    if ((rc = verify_main(ctx, (const uint8_t*)ctx->in_d.p, n_agg, (uint8_t*)ctx->out_a.p, s))) return rc;
+    if ((rc = verify_fork(ctx, ctx->slot[0], P, (const uint8_t*)ctx->in_e.p, n_agg, s))) return rc;
+    if ((rc = verify_main(ctx, ctx->slot[0], (const uint8_t*)ctx->in_d.p, n_agg, (uint8_t*)ctx->out_a.p, s))) return rc;
     std::vector<uint8_t> tok(n_agg);
     CK(cudaMemcpyAsync(tok.data(), ctx->out_a.p, n_agg, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -701,6 +775,7 @@ int b2_vote_weights_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, void* stream) {
                                                                   ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder);
     }
     CKL(ctx);
+    CK(cudaEventRecord(ctx->ev_votes_done, s));
     return B2_OK;
 }
 

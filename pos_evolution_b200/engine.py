@@ -229,6 +229,20 @@ class Engine:
                                        d_msgs.data_ptr(), d_target_epoch.data_ptr(), d_block_idx.data_ptr(), n_agg, d_sigs.numel() // 96,
                                        d_agg_sig.data_ptr(), d_agg_status.data_ptr(), d_ok.data_ptr(), self._stream()))
 
+    def epoch_start_dev(self, slot, d_sigs, d_members, d_off, d_bits, d_msgs, d_agg_status):
+        n_agg = d_off.numel() - 1
+        self._ck(self.lib.b2_epoch_start_dev(self.h, int(slot), d_sigs.data_ptr(), d_members.data_ptr(), d_off.data_ptr(), d_bits.data_ptr(),
+                                             d_bits.shape[1], d_msgs.data_ptr(), n_agg, d_sigs.numel() // 96, d_agg_status.data_ptr(), self._stream()))
+
+    def epoch_tail_dev(self, slot, d_members, d_off, d_bits, d_target_epoch, d_block_idx, d_agg_sig, d_agg_status, d_ok):
+        n_agg = d_off.numel() - 1
+        self._ck(self.lib.b2_epoch_tail_dev(self.h, int(slot), d_members.data_ptr(), d_off.data_ptr(), d_bits.data_ptr(), d_bits.shape[1],
+                                            d_target_epoch.data_ptr(), d_block_idx.data_ptr(), n_agg, d_agg_sig.data_ptr(), d_agg_status.data_ptr(),
+                                            d_ok.data_ptr()))
+
+    def epoch_wait_dev(self, slot):
+        self._ck(self.lib.b2_epoch_wait_dev(self.h, int(slot), self._stream()))
+
     def vote_weights_dev(self, d_votes):
         self._ck(self.lib.b2_vote_weights_dev(self.h, d_votes.data_ptr(), self._stream()))
 

@@ -5,18 +5,36 @@ One call processes a whole epoch of attestations for the validators this rank ow
   --FastAggregateVerify (registry-indexed pubkey gather + hash-to-G2 + pairing)--> verdicts
   --update_latest_messages (accepted aggregates only)--> LMD table on the device
   --get_weight scatter--> per-block direct votes  [--NCCL all-reduce over ranks--]  --get_head--> head index.
-(pos-evolution.md:722-754, :963-979, :1102-1116, :1435-1441.)  Device-resident inputs
-(`process_epoch_dev`) are torch CUDA tensors; `process_epoch_host` takes pinned host tensors and does
-the H2D/D2H copies itself -- that is the end-to-end call bench.py times.
+(pos-evolution.md:722-754, :963-979, :1102-1116, :1435-1441.)
 
-Multi-GPU: validators (and with them committees / aggregates) are sharded across ranks with no
-data-path exchange until the vote weights: u64[n_blocks] direct votes are summed with one
-torch.distributed all_reduce (NCCL over NVLink; int64 two's-complement sum == u64 sum), after which
-every rank finishes get_head on its replica of the block tree.
+Two ways to drive it:
+  * `process_epoch_dev` / `process_epoch_host`: synchronous in stream order, one epoch at a time;
+  * `submit_dev` / `submit_host` + `drain`: software-pipelined over two slots.  The signature decompression of
+    epoch k+1 (grid-filling, integer-pipe bound) overlaps with the latency-bound tail of epoch k (subgroup check,
+    second Miller loop, final exponentiation, LMD update) which runs on the library's own high-priority stream, and in
+    the host form the H2D copy of epoch k+1 overlaps with the compute of epoch k.  Results come back one call later.
+
+Multi-GPU: validators (and with them committees / aggregates) are sharded across ranks with no data-path exchange
+until the vote weights: u64[n_blocks] direct votes are summed with one torch.distributed all_reduce (NCCL over NVLink;
+int64 two's-complement sum == u64 sum), after which every rank finishes get_head on its replica of the block tree.
 """
 import torch
 
 from .engine import Engine
+
+
+class _Ticket:
+    """Result of one submitted epoch: verdict bytes + head index, valid after .wait()."""
+
+    def __init__(self, d_ok, d_head, h_ok=None, h_head=None, event=None):
+        self.d_ok, self.d_head, self.h_ok, self.h_head, self.event = d_ok, d_head, h_ok, h_head, event
+
+    def wait(self):
+        if self.event is not None:
+            self.event.synchronize()
+            return self.h_ok, int(self.h_head[0])
+        torch.cuda.current_stream().synchronize()
+        return self.d_ok, int(self.d_head[0])
 
 
 class EpochProcessor:
@@ -26,57 +44,123 @@ class EpochProcessor:
         self.pg = process_group
         self.n_agg, self.n_sig, self.n_blocks = n_agg, n_sig, n_blocks
         d = self.dev
-        self.d_agg_sig = torch.zeros((n_agg, 96), dtype=torch.uint8, device=d)
-        self.d_agg_status = torch.zeros(n_agg, dtype=torch.int32, device=d)
-        self.d_ok = torch.zeros(n_agg, dtype=torch.uint8, device=d)
-        self.d_votes = torch.zeros(n_blocks, dtype=torch.int64, device=d)
-        self.d_head = torch.zeros(1, dtype=torch.int32, device=d)
-        # staging for the host entry point
-        self.d_sigs = torch.zeros((n_sig, 96), dtype=torch.uint8, device=d)
-        self.d_bits = torch.zeros((n_agg, bits_stride), dtype=torch.uint8, device=d)
-        self.d_msgs = torch.zeros((n_agg, 32), dtype=torch.uint8, device=d)
-        self.d_target_epoch = torch.zeros(n_agg, dtype=torch.int64, device=d)
-        self.d_block_idx = torch.zeros(n_agg, dtype=torch.int32, device=d)
-        pin = torch.cuda.is_available()
-        self.h_ok = torch.zeros(n_agg, dtype=torch.uint8, pin_memory=pin)
-        self.h_head = torch.zeros(1, dtype=torch.int32, pin_memory=pin)
+        cuda = self.dev.type == "cuda"
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=d)            # noqa: E731
+        self.d_agg_sig = [z((n_agg, 96), torch.uint8) for _ in range(2)]
+        self.d_agg_status = [z(n_agg, torch.int32) for _ in range(2)]
+        self.d_ok = [z(n_agg, torch.uint8) for _ in range(2)]
+        self.d_head = [z(1, torch.int32) for _ in range(2)]
+        self.d_votes = z(n_blocks, torch.int64)
+        # per-slot copies of everything the asynchronous tail / side streams read, and staging for the host entry points
+        self.s_sigs = [z((n_sig, 96), torch.uint8) for _ in range(2)]
+        self.s_bits = [z((n_agg, bits_stride), torch.uint8) for _ in range(2)]
+        self.s_msgs = [z((n_agg, 32), torch.uint8) for _ in range(2)]
+        self.s_epoch = [z(n_agg, torch.int64) for _ in range(2)]
+        self.s_blk = [z(n_agg, torch.int32) for _ in range(2)]
+        self.h_ok = [torch.zeros(n_agg, dtype=torch.uint8, pin_memory=cuda) for _ in range(2)]
+        self.h_head = [torch.zeros(1, dtype=torch.int32, pin_memory=cuda) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=d) if cuda else None
+        self.k = 0
+        self._pending = None          # (slot, fork-choice args, host?) of the epoch whose tail is in flight
 
     def set_committees(self, members, off):
         """members u32[n_sig] (committee order), off u32[n_agg+1]; signature j belongs to member j."""
         self.d_members = torch.as_tensor(members.astype("int32"), device=self.dev)
         self.d_off = torch.as_tensor(off.astype("int32"), device=self.dev)
 
+    # ------------------------------------------------------------------ synchronous form
     def process_epoch_dev(self, d_sigs, d_bits, d_msgs, d_target_epoch, d_block_idx, justified_idx=0, boost_idx=-1, boost_score=0):
         e = self.eng
         if hasattr(e, "epoch_dev"):
-            e.epoch_dev(d_sigs, self.d_members, self.d_off, d_bits, d_msgs, d_target_epoch, d_block_idx, self.d_agg_sig, self.d_agg_status, self.d_ok)
+            e.epoch_dev(d_sigs, self.d_members, self.d_off, d_bits, d_msgs, d_target_epoch, d_block_idx, self.d_agg_sig[0], self.d_agg_status[0], self.d_ok[0])
         else:                                           # engines without the fused entry point (tests' stand-ins)
-            e.aggregate_dev(d_sigs, self.d_off, self.d_agg_sig, self.d_agg_status)
-            e.fast_aggregate_verify_dev(self.d_members, self.d_off, d_bits, d_msgs, self.d_agg_sig, self.d_ok)
-            e.latest_messages_update_dev(self.d_members, self.d_off, d_bits, d_target_epoch, d_block_idx, self.d_ok)
+            e.aggregate_dev(d_sigs, self.d_off, self.d_agg_sig[0], self.d_agg_status[0])
+            e.fast_aggregate_verify_dev(self.d_members, self.d_off, d_bits, d_msgs, self.d_agg_sig[0], self.d_ok[0])
+            e.latest_messages_update_dev(self.d_members, self.d_off, d_bits, d_target_epoch, d_block_idx, self.d_ok[0])
+        self._fork_choice(0, justified_idx, boost_idx, boost_score)
+        return self.d_ok[0], self.d_head[0]
+
+    def _fork_choice(self, slot, justified_idx, boost_idx, boost_score):
+        e = self.eng
         e.vote_weights_dev(self.d_votes)
         if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
             torch.distributed.all_reduce(self.d_votes, group=self.pg)
-        e.head_from_votes_dev(self.d_votes, self.d_head, justified_idx, boost_idx, boost_score)
-        return self.d_ok, self.d_head
+        e.head_from_votes_dev(self.d_votes, self.d_head[slot], justified_idx, boost_idx, boost_score)
 
     def process_epoch_host(self, h_sigs, h_bits, h_msgs, h_target_epoch, h_block_idx, justified_idx=0, boost_idx=-1, boost_score=0):
-        """Pinned host tensors in, (verdict bytes, head index) out on the host."""
-        self.d_sigs.copy_(h_sigs, non_blocking=True)
-        self.d_bits.copy_(h_bits, non_blocking=True)
-        self.d_msgs.copy_(h_msgs, non_blocking=True)
-        self.d_target_epoch.copy_(h_target_epoch, non_blocking=True)
-        self.d_block_idx.copy_(h_block_idx, non_blocking=True)
-        self.process_epoch_dev(self.d_sigs, self.d_bits, self.d_msgs, self.d_target_epoch, self.d_block_idx, justified_idx, boost_idx, boost_score)
-        self.h_ok.copy_(self.d_ok, non_blocking=True)
-        self.h_head.copy_(self.d_head, non_blocking=True)
+        """Pinned host tensors in, (verdict bytes, head index) out on the host; returns when the epoch is done."""
+        s = 0
+        self.s_sigs[s].copy_(h_sigs, non_blocking=True)
+        self.s_bits[s].copy_(h_bits, non_blocking=True)
+        self.s_msgs[s].copy_(h_msgs, non_blocking=True)
+        self.s_epoch[s].copy_(h_target_epoch, non_blocking=True)
+        self.s_blk[s].copy_(h_block_idx, non_blocking=True)
+        self.process_epoch_dev(self.s_sigs[s], self.s_bits[s], self.s_msgs[s], self.s_epoch[s], self.s_blk[s], justified_idx, boost_idx, boost_score)
+        self.h_ok[s].copy_(self.d_ok[0], non_blocking=True)
+        self.h_head[s].copy_(self.d_head[0], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.h_ok, int(self.h_head[0])
+        return self.h_ok[s], int(self.h_head[s][0])
+
+    # ------------------------------------------------------------------ pipelined form
+    def _finish_pending(self):
+        """Fork choice (and, for host submissions, the D2H of the results) of the epoch whose tail is in flight."""
+        if self._pending is None:
+            return None
+        slot, fc, host = self._pending
+        self._pending = None
+        self.eng.epoch_wait_dev(slot)
+        self._fork_choice(slot, *fc)
+        if not host:
+            return _Ticket(self.d_ok[slot], self.d_head[slot])
+        self.h_ok[slot].copy_(self.d_ok[slot], non_blocking=True)
+        self.h_head[slot].copy_(self.d_head[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return _Ticket(self.d_ok[slot], self.d_head[slot], self.h_ok[slot], self.h_head[slot], ev)
+
+    def _submit(self, slot, d_sigs, d_bits, d_msgs, fc, host):
+        e = self.eng
+        e.epoch_start_dev(slot, d_sigs, self.d_members, self.d_off, d_bits, d_msgs, self.d_agg_status[slot])
+        done = self._finish_pending()                     # epoch k-1: after start(k) so that its wait does not stall the decompression
+        e.epoch_tail_dev(slot, self.d_members, self.d_off, d_bits, self.s_epoch[slot], self.s_blk[slot], self.d_agg_sig[slot],
+                         self.d_agg_status[slot], self.d_ok[slot])
+        self._pending = (slot, fc, host)
+        self.k += 1
+        return done
+
+    def submit_dev(self, d_sigs, d_bits, d_msgs, d_target_epoch, d_block_idx, justified_idx=0, boost_idx=-1, boost_score=0):
+        """Enqueue one epoch (device-resident inputs, which must stay untouched until its ticket is returned).
+        Returns the ticket of the PREVIOUS epoch (None for the first call)."""
+        slot = self.k & 1
+        self.eng.epoch_wait_dev(slot)                     # the slot's previous tail must be done before its small inputs are replaced
+        self.s_epoch[slot].copy_(d_target_epoch)
+        self.s_blk[slot].copy_(d_block_idx)
+        return self._submit(slot, d_sigs, d_bits, d_msgs, (justified_idx, boost_idx, boost_score), False)
+
+    def submit_host(self, h_sigs, h_bits, h_msgs, h_target_epoch, h_block_idx, justified_idx=0, boost_idx=-1, boost_score=0):
+        """Pinned host tensors in.  The H2D copies go on a separate stream so that they overlap with the previous epoch."""
+        slot = self.k & 1
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            self.eng.epoch_wait_dev(slot)                 # copy stream waits for the slot's previous tail (it reads bits/epoch/blk)
+            self.s_sigs[slot].copy_(h_sigs, non_blocking=True)
+            self.s_bits[slot].copy_(h_bits, non_blocking=True)
+            self.s_msgs[slot].copy_(h_msgs, non_blocking=True)
+            self.s_epoch[slot].copy_(h_target_epoch, non_blocking=True)
+            self.s_blk[slot].copy_(h_block_idx, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        cur.wait_event(ev)
+        return self._submit(slot, self.s_sigs[slot], self.s_bits[slot], self.s_msgs[slot], (justified_idx, boost_idx, boost_score), True)
+
+    def drain(self):
+        """Finish the last submitted epoch; returns its ticket."""
+        return self._finish_pending()
 
     @property
     def h2d_bytes(self):
-        return (self.d_sigs.numel() + self.d_bits.numel() + self.d_msgs.numel() + 8 * self.d_target_epoch.numel() + 4 * self.d_block_idx.numel())
+        return (self.s_sigs[0].numel() + self.s_bits[0].numel() + self.s_msgs[0].numel() + 8 * self.s_epoch[0].numel() + 4 * self.s_blk[0].numel())
 
     @property
     def d2h_bytes(self):
-        return self.h_ok.numel() + 4
+        return self.h_ok[0].numel() + 4
