@@ -168,7 +168,7 @@ def build_world(eng, rank, np, PS):
     valid = eng.registry_load(pk, eff, active)
     assert int(valid.sum()) == N_VAL
     seed = _h(b"b200pos/epoch-seed" + rank.to_bytes(8, "little"))
-    perm = PS.shuffle_permutation(N_VAL, seed, 90)                      # compute_shuffled_index for all i (pos-evolution.md:513-534)
+    perm = eng.shuffle_committees(seed, N_VAL, 90)                      # compute_shuffled_index for all i (pos-evolution.md:513-534), on the GPU
     members = perm.astype(np.uint32)                                    # active set = all validators, committee k = members[512k : 512k+512]
     off = (np.arange(N_AGG + 1, dtype=np.uint64) * COMMITTEE_SIZE).astype(np.uint32)
     msgs = np.frombuffer(b"".join(_h(b"b200pos/signing-root" + rank.to_bytes(4, "little") + a.to_bytes(4, "little")) for a in range(N_AGG)),

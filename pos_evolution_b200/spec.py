@@ -287,7 +287,10 @@ class Spec:
         if key not in self._committee_cache:
             if len(self._committee_cache) > 8:
                 self._committee_cache.clear()
-            self._committee_cache[key] = shuffle_permutation(n, seed, self.p.SHUFFLE_ROUND_COUNT)
+            if hasattr(self.engine, "shuffle_committees"):      # SHA-256 + swap-or-not rounds on the GPU (k_shuffle_*)
+                self._committee_cache[key] = self.engine.shuffle_committees(seed, n, self.p.SHUFFLE_ROUND_COUNT)
+            else:                                               # engine stand-ins of the CPU tests
+                self._committee_cache[key] = shuffle_permutation(n, seed, self.p.SHUFFLE_ROUND_COUNT)
         return self._committee_cache[key]
 
     def epoch_committees(self, state, epoch):

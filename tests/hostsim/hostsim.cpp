@@ -184,3 +184,5 @@ void hs_core_verify(const uint32_t* pk_jac, const uint8_t* pk_status, const uint
 }
 
 }  // extern "C"
+
+extern "C" void hs_fp_sqr(const uint32_t* a, uint32_t* r) { st(r, fp_sqr(ld<fp>(a))); }

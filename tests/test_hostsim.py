@@ -224,3 +224,16 @@ def test_pairing_bit_exact_vs_oracle():
     out = np.zeros(144, dtype=np.uint32)
     lib.hs_pairing(hs.buf(bytes([0xC0]) + bytes(47)), hs.buf(g2_compress(G2)), hs.ptr(out), 1, 0)
     assert hs.fp12_v(out) == F12_ONE
+
+
+def test_fp_sqr_dedicated():
+    edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (1 << 380), (1 << 381) - 1 - ((1 << 381) - 1 >= P) * ((1 << 381) - P), hs.RMONT % P,
+            int("ffffffff" * 11 + "0", 16) % P, int("0fffffffffffffff" * 6, 16) % P]
+    for a in edge + [rfp() for _ in range(5000)]:
+        assert hs.fp_v(call(lib.hs_fp_sqr, hs.fp_m(a), out_words=12)) == a * a % P
+    # raw limb patterns (the Montgomery image is what the chains see): all-ones limbs below p, alternating, sparse
+    for raw in (P - 1, P - 2, int("ffffffff" * 11, 16), int("ffffffff00000000" * 5 + "ffffffff", 16), 1 << 352, (1 << 352) - 1):
+        raw %= P
+        arr = np.array(hs.limbs(raw), dtype=np.uint32)
+        got = call(lib.hs_fp_sqr, arr, out_words=12)
+        assert sum(int(x) << (32 * i) for i, x in enumerate(got)) == raw * raw * hs.RINV % P
