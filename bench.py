@@ -322,14 +322,14 @@ def run_gpu(args):
     torch.cuda.synchronize()
     ks0.record()
     for _ in range(reps):
-        eng.aggregate_dev(d_sigs, ep.d_off, ep.d_agg_sig, ep.d_agg_status)
+        eng.aggregate_dev(d_sigs, ep.d_off, ep.d_agg_sig[0], ep.d_agg_status[0])
     ks1.record()
     torch.cuda.synchronize()
     ms_agg = ks0.elapsed_time(ks1) / reps
     kv0, kv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kv0.record()
     for _ in range(reps):
-        eng.fast_aggregate_verify_dev(ep.d_members, ep.d_off, d_bits, d_msgs, ep.d_agg_sig, ep.d_ok)
+        eng.fast_aggregate_verify_dev(ep.d_members, ep.d_off, d_bits, d_msgs, ep.d_agg_sig[0], ep.d_ok[0])
     kv1.record()
     torch.cuda.synchronize()
     ms_verify = kv0.elapsed_time(kv1) / reps

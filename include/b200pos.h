@@ -86,6 +86,9 @@ int b2_sign(b2_ctx* ctx, const uint32_t* sk8, const uint32_t* msg_idx, uint64_t 
 /* H(m) compressed, for tests (hash_to_G2 with the POP ciphersuite tag) */
 int b2_hash_to_g2(b2_ctx* ctx, const uint8_t* msg32, uint32_t n_msg, uint8_t* out96);
 
+/* `hash` of the spec (SHA-256; pos-evolution.md:486, :522, :525), batched over n messages of msg_len bytes each */
+int b2_sha256_batch(b2_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint64_t n, uint8_t* out32);
+
 /* ---- committees: compute_committee / compute_shuffled_index (pos-evolution.md:495-534) for a whole epoch.
  * members_out[i] = active[compute_shuffled_index(i, n_active, seed)] (active == NULL: identity), so committee k of
  * `count` is members_out[n*k/count .. n*(k+1)/count).  SHA-256 and the swap-or-not rounds run on the GPU. */

@@ -92,6 +92,7 @@ template <class T> static int dev_alloc(b2_ctx* ctx, T** p, size_t count) {
     CK(cudaMalloc((void**)p, std::max<size_t>(count * sizeof(T), 256)));
     return B2_OK;
 }
+#define B2_TEAM_SMEM (B2_TEAMS_PER_WARP * sizeof(team_ws))
 static inline unsigned blocks_for(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 extern "C" {
@@ -374,9 +375,9 @@ static int verify_fork(b2_ctx* ctx, vslot& V, const pk_source& P, const uint8_t*
         CKL(ctx);
     }
     CK(cudaStreamWaitEvent(ctx->s_aux[1], V.ev_join0, 0));
-    k_miller<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[1]>>>((const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p,
-                                                             (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p, (const uint8_t*)V.sflag.p, n_agg,
-                                                             (uint32_t*)V.f.p, 1);
+    k_miller_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, ctx->s_aux[1]>>>(
+        (const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p, (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p,
+        (const uint8_t*)V.sflag.p, n_agg, (uint32_t*)V.f.p, 1);
     CKL(ctx);
     CK(cudaEventRecord(V.ev_join1, ctx->s_aux[1]));
     return B2_OK;
@@ -387,12 +388,13 @@ static int verify_main(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, uint32_t n
         k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, s>>>(d_sig96, n_agg, (uint32_t*)V.saff.p, (uint8_t*)V.sflag.p);
         CKL(ctx);
     }
-    k_miller<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p,
-                                                  (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p, (const uint8_t*)V.sflag.p, n_agg,
-                                                  (uint32_t*)V.f.p, 2);
+    k_miller_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, s>>>(
+        (const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p, (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p,
+        (const uint8_t*)V.sflag.p, n_agg, (uint32_t*)V.f.p, 2);
     CKL(ctx);
     CK(cudaStreamWaitEvent(s, V.ev_join1, 0));
-    k_final_verdict<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)V.f.p, (const uint8_t*)V.pkst.p, (const uint8_t*)V.sflag.p, n_agg, d_ok);
+    k_final_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, s>>>((const uint32_t*)V.f.p, (const uint8_t*)V.pkst.p,
+                                                                              (const uint8_t*)V.sflag.p, n_agg, d_ok);
     CKL(ctx);
     return B2_OK;
 }
@@ -586,6 +588,21 @@ int b2_sign(b2_ctx* ctx, const uint32_t* sk8, const uint32_t* msg_idx, uint64_t 
     return B2_OK;
 }
 
+// ------------------------------------------------------------------------------------------ batched SHA-256
+int b2_sha256_batch(b2_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint64_t n, uint8_t* out32) {
+    REQUIRE(ctx && out32 && n > 0 && (msg_len == 0 || msgs), "sha256_batch: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_a, (size_t)n * msg_len + 16)) || (rc = ensure(ctx, ctx->out_a, (size_t)n * 32))) return rc;
+    if (msg_len) CK(cudaMemcpyAsync(ctx->in_a.p, msgs, (size_t)n * msg_len, cudaMemcpyHostToDevice, s));
+    k_sha256_fixed<<<blocks_for(n, 128), 128, 0, s>>>((const uint8_t*)ctx->in_a.p, msg_len, n, (uint8_t*)ctx->out_a.p);
+    CKL(ctx);
+    CK(cudaMemcpyAsync(out32, ctx->out_a.p, (size_t)n * 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------------------------------ committee shuffle
 int b2_shuffle_committees_dev(b2_ctx* ctx, const uint8_t* d_seed32, const uint32_t* d_active, uint32_t n_active, uint32_t rounds,
                               uint32_t* d_members_out, void* stream) {
@@ -597,7 +614,7 @@ int b2_shuffle_committees_dev(b2_ctx* ctx, const uint8_t* d_seed32, const uint32
     int rc;
     if ((rc = ensure(ctx, ctx->sc_shuf, (size_t)rounds * nblk * 32 + 16)) || (rc = ensure(ctx, ctx->sc_pivot, (size_t)rounds * 8 + 16))) return rc;
     if (rounds) {
-        k_shuffle_sources<<<blocks_for((uint64_t)rounds * nblk, 128), 128, 0, s>>>(d_seed32, n_active, rounds, nblk, (uint8_t*)ctx->sc_shuf.p,
+        k_shuffle_sources<<<blocks_for((uint64_t)rounds * (nblk + 1), 128), 128, 0, s>>>(d_seed32, n_active, rounds, nblk, (uint8_t*)ctx->sc_shuf.p,
                                                                                   (unsigned long long*)ctx->sc_pivot.p);
         CKL(ctx);
     }
@@ -836,3 +853,12 @@ int b2_get_head(b2_ctx* ctx, uint32_t justified_idx, int32_t boost_idx, uint64_t
 }
 
 }  // extern "C"
+
+// debug helper (not part of the public header): read back the shuffle's per-round source table and pivots
+extern "C" int b2_debug_shuffle_tables(b2_ctx* ctx, uint8_t* src_out, size_t src_bytes, uint64_t* pivots_out, uint32_t rounds) {
+    if (!ctx || !ctx->sc_shuf.p || !ctx->sc_pivot.p) return B2_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(src_out, ctx->sc_shuf.p, src_bytes, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pivots_out, ctx->sc_pivot.p, (size_t)rounds * 8, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}

@@ -293,14 +293,16 @@ __global__ void __launch_bounds__(64) k_g2_compress_aff(const uint32_t* __restri
 
 // ------------------------------------------------------------------------------------------ committee shuffle
 // compute_shuffled_index (/root/reference/pos-evolution.md:513-534) for every index of the active set at once.
-// Stage 1: one thread per (round, 256-index block): source = SHA256(seed || round || LE32(block)); thread (round, 0) also
-// derives pivot = LE64(SHA256(seed || round)[0:8]) mod n.  Stage 2: one thread per index walks the rounds in order
+// Stage 1: one thread per hash: source = SHA256(seed || round || LE32(block)) for every 256-index block of every round, and
+// pivot = LE64(SHA256(seed || round)[0:8]) mod n per round.  Stage 2: one thread per index walks the rounds in order
 // (swap-or-not), reading one source bit per round from the 32 n/256-byte per-round table (L1/L2 resident).
 __global__ void __launch_bounds__(128) k_shuffle_sources(const uint8_t* __restrict__ seed32, uint32_t n, uint32_t rounds, uint32_t nblk,
                                                           uint8_t* src, unsigned long long* pivots) {
+    // one hash per thread: items 0..nblk-1 of a round are its source blocks, item nblk is its pivot
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= rounds * nblk) return;
-    uint32_t r = t / nblk, blk = t % nblk;
+    if (t >= rounds * (nblk + 1)) return;
+    const uint32_t r = t / (nblk + 1), blk = t % (nblk + 1);
+    const bool is_pivot = blk == nblk;
     uint8_t buf[37];
 #pragma unroll 1
     for (int i = 0; i < 32; i++) buf[i] = seed32[i];
@@ -312,19 +314,17 @@ __global__ void __launch_bounds__(128) k_shuffle_sources(const uint8_t* __restri
     sha256_ctx c;
     uint8_t out[32];
     sha256_init(c);
-    sha256_update(c, buf, 37);
+    sha256_update(c, buf, is_pivot ? 33u : 37u);
     sha256_final(c, out);
-    uint8_t* dst = src + ((uint64_t)r * nblk + blk) * 32;
-#pragma unroll 1
-    for (int i = 0; i < 32; i++) dst[i] = out[i];
-    if (blk == 0) {
-        sha256_init(c);
-        sha256_update(c, buf, 33);
-        sha256_final(c, out);
+    if (is_pivot) {
         unsigned long long v = 0;
-#pragma unroll
+#pragma unroll 1
         for (int i = 7; i >= 0; i--) v = (v << 8) | out[i];
         pivots[r] = v % n;
+    } else {
+        uint8_t* dst = src + ((uint64_t)r * nblk + blk) * 32;
+#pragma unroll 1
+        for (int i = 0; i < 32; i++) dst[i] = out[i];
     }
 }
 // perm[i] = compute_shuffled_index(i); members_out[i] = active[perm[i]] (active == nullptr: identity)
@@ -570,3 +570,98 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
 }
 
 }  // namespace b2
+
+// ------------------------------------------------------------------------------------------ K5/K6, 3-lane team versions
+#include "team.cuh"
+namespace b2 {
+
+#define B2_TEAMS_PER_WARP 10         // 30 of 32 lanes; 10 * sizeof(team_ws) = 48 960 B of shared memory per (one-warp) block
+
+// value index `item`: mode 0: item in [0, 2n): even = pubkey half, odd = signature half; mode 1/2: item = aggregate
+__global__ void __launch_bounds__(32) k_miller_team(const uint32_t* __restrict__ pk_jac, const uint8_t* __restrict__ pk_status,
+                                                     const uint32_t* __restrict__ h_aff, const uint8_t* __restrict__ hflag,
+                                                     const uint32_t* __restrict__ s_aff, const uint8_t* __restrict__ sflag, uint32_t n_agg,
+                                                     uint32_t* f_out, int mode) {
+    extern __shared__ unsigned long long team_smem[];
+    team_ws* wsv = reinterpret_cast<team_ws*>(team_smem);
+    const int lane = threadIdx.x, tt = lane / 3, l = lane % 3;
+    const uint32_t n_items = mode == 0 ? 2 * n_agg : n_agg;
+    uint32_t item = blockIdx.x * B2_TEAMS_PER_WARP + tt;
+    if (tt >= B2_TEAMS_PER_WARP || item >= n_items) return;
+    uint32_t t = mode == 0 ? item : 2 * item + (uint32_t)(mode - 1);
+    const uint32_t a = t >> 1;
+    team tm = {l, 7u << (3 * tt), nullptr};
+    team_ws* ws = wsv + tt;
+    if (t & 1) {
+        const uint8_t sf = sflag[a];
+        if (sf == SIG_INVALID) {
+            if (l == 0) ws->f = fp12_one();
+            team_sync(tm);
+        } else {
+            g1_jac ng;
+            ng.x = fp_load_const(C_G1X);
+            ng.y = fp_load_const(C_G1Y_NEG);
+            ng.z = fp_one();
+            team_miller_loop(tm, ws, ng, load_g2_aff(s_aff + 48 * (uint64_t)a), sf == SIG_INFINITY);
+        }
+    } else {
+        if (pk_status[a] != PK_OK) {
+            if (l == 0) ws->f = fp12_one();
+            team_sync(tm);
+        } else {
+            team_miller_loop(tm, ws, load_g1_jac(pk_jac + 36 * (uint64_t)a), load_g2_aff(h_aff + 48 * (uint64_t)a), hflag[a] != 0);
+        }
+    }
+    uint32_t* o = f_out + 144 * (uint64_t)t;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&ws->f);
+#pragma unroll 1
+    for (int k = l; k < 144; k += 3) o[k] = w[k];
+}
+
+__global__ void __launch_bounds__(32) k_final_team(const uint32_t* __restrict__ f_in, const uint8_t* __restrict__ pk_status,
+                                                    const uint8_t* __restrict__ sflag, uint32_t n_agg, uint8_t* ok) {
+    extern __shared__ unsigned long long team_smem[];
+    team_ws* wsv = reinterpret_cast<team_ws*>(team_smem);
+    const int lane = threadIdx.x, tt = lane / 3, l = lane % 3;
+    const uint32_t a = blockIdx.x * B2_TEAMS_PER_WARP + tt;
+    if (tt >= B2_TEAMS_PER_WARP || a >= n_agg) return;
+    team tm = {l, 7u << (3 * tt), nullptr};
+    team_ws* ws = wsv + tt;
+    if (pk_status[a] != PK_OK || sflag[a] == SIG_INVALID) {
+        if (l == 0) ok[a] = 0;
+        return;
+    }
+    const uint32_t* p = f_in + 288 * (uint64_t)a;
+    uint32_t* w0 = reinterpret_cast<uint32_t*>(&ws->g);
+    uint32_t* w1 = reinterpret_cast<uint32_t*>(&ws->h);
+#pragma unroll 1
+    for (int k = l; k < 144; k += 3) {
+        w0[k] = p[k];
+        w1[k] = p[144 + k];
+    }
+    team_sync(tm);
+    team_fp12_mul(tm, ws, &ws->f, &ws->g, &ws->h);
+    team_final_exponentiation(tm, ws);
+    if (l == 0) ok[a] = fp12_is_one(ws->f) ? 1 : 0;
+}
+
+}  // namespace b2
+
+// ------------------------------------------------------------------------------------------ batched SHA-256 (fixed-length messages)
+// `hash` of the spec (pos-evolution.md:486, :522, :525): n messages of msg_len bytes each -> n digests.  Building block of
+// the committee shuffle and of device-side SSZ merkleization.
+namespace b2 {
+__global__ void __launch_bounds__(128) k_sha256_fixed(const uint8_t* __restrict__ in, uint32_t msg_len, uint64_t n, uint8_t* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sha256_ctx c;
+    uint8_t d[32];
+    sha256_init(c);
+    sha256_update(c, in + i * msg_len, msg_len);
+    sha256_final(c, d);
+#pragma unroll 1
+    for (int k = 0; k < 32; k++) out[32 * i + k] = d[k];
+}
+}  // namespace b2
+static_assert(B2_TEAMS_PER_WARP * 3 <= 32, "a warp holds at most 10 three-lane teams");
+static_assert(B2_TEAMS_PER_WARP * sizeof(b2::team_ws) <= 48 * 1024, "team workspaces must fit the default dynamic shared memory limit");

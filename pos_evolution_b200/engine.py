@@ -150,6 +150,14 @@ class Engine:
         self._ck(self.lib.b2_hash_to_g2(self.h, _p(msgs), msgs.shape[0], _p(out)))
         return out
 
+    def sha256_batch(self, msgs, msg_len: int):
+        """SHA-256 of n fixed-length messages (uint8[n, msg_len]) on the GPU -> uint8[n, 32]."""
+        m = _c(msgs, np.uint8).reshape(-1, msg_len) if msg_len else np.zeros((int(msgs), 0), dtype=np.uint8)
+        n = m.shape[0]
+        out = np.zeros((n, 32), dtype=np.uint8)
+        self._ck(self.lib.b2_sha256_batch(self.h, _p(m) if msg_len else None, msg_len, n, _p(out)))
+        return out
+
     def shuffle_committees(self, seed32: bytes, n_active: int, rounds: int, active=None):
         """members[i] = active[compute_shuffled_index(i, n_active, seed)] for the whole active set, on the GPU."""
         seed = np.frombuffer(bytes(seed32), dtype=np.uint8)

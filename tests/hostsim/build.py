@@ -14,7 +14,7 @@ def build(force=False):
     srcs = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "hostsim.cpp")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in srcs):
         return OUT
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I", CSRC,
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-x", "c++", "-I", CSRC,
            os.path.join(HERE, "hostsim.cpp"), "-o", OUT]
     subprocess.check_call(cmd)
     return OUT

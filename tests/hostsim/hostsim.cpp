@@ -186,3 +186,52 @@ void hs_core_verify(const uint32_t* pk_jac, const uint8_t* pk_status, const uint
 }  // extern "C"
 
 extern "C" void hs_fp_sqr(const uint32_t* a, uint32_t* r) { st(r, fp_sqr(ld<fp>(a))); }
+
+// ---- team (3-lane cooperative) pairing: three host threads + a barrier stand in for three SIMT lanes
+#include <pthread.h>
+
+#include <thread>
+
+#include "team.cuh"
+namespace b2 {
+void host_team_barrier(void* b) { pthread_barrier_wait((pthread_barrier_t*)b); }
+}
+extern "C" int hs_team_pairing(const uint8_t* p48, const uint8_t* q96, uint32_t* out, int do_final_exp, int scale_p) {
+    g1_aff pa;
+    g2_aff qa;
+    int sp = g1_decompress(p48, pa), sq = g2_decompress(q96, qa);
+    if (sp == DEC_BAD || sq == DEC_BAD) return 1;
+    g1_jac pj = sp == DEC_INF ? pt_inf<fp>() : pt_from_affine(pa);
+    if (scale_p && sp == DEC_OK) pj = pt_add_mixed(pt_dbl(pj), pa);
+    team_ws* ws = new team_ws();
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, nullptr, 3);
+    std::thread th[3];
+    for (int l = 0; l < 3; l++)
+        th[l] = std::thread([&, l]() {
+            team tm = {l, 0u, &bar};
+            team_miller_loop(tm, ws, pj, qa, sq == DEC_INF);
+            if (do_final_exp) team_final_exponentiation(tm, ws);
+        });
+    for (int l = 0; l < 3; l++) th[l].join();
+    st(out, ws->f);
+    pthread_barrier_destroy(&bar);
+    delete ws;
+    return 0;
+}
+extern "C" void hs_team_final_exp(const uint32_t* in, uint32_t* out) {
+    team_ws* ws = new team_ws();
+    ws->f = ld<fp12>(in);
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, nullptr, 3);
+    std::thread th[3];
+    for (int l = 0; l < 3; l++)
+        th[l] = std::thread([&, l]() {
+            team tm = {l, 0u, &bar};
+            team_final_exponentiation(tm, ws);
+        });
+    for (int l = 0; l < 3; l++) th[l].join();
+    st(out, ws->f);
+    pthread_barrier_destroy(&bar);
+    delete ws;
+}

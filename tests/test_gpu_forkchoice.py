@@ -100,3 +100,15 @@ def test_gpu_shuffle_matches_oracle(eng, n, rounds):
     assert np.array_equal(eng.shuffle_committees(seed, n, rounds), ref)
     active = (np.arange(n, dtype=np.uint32) * 3 + 7).astype(np.uint32)
     assert np.array_equal(eng.shuffle_committees(seed, n, rounds, active), active[ref])
+
+
+@pytest.mark.parametrize("length", [0, 1, 32, 33, 37, 55, 56, 63, 64, 65, 100, 143])
+def test_gpu_sha256_batch(eng, length):
+    import hashlib
+    rng = np.random.default_rng(length)
+    n = 70
+    msgs = rng.integers(0, 256, size=(n, length), dtype=np.uint8) if length else n
+    out = eng.sha256_batch(msgs, length)
+    for i in range(n):
+        m = bytes(msgs[i]) if length else b""
+        assert bytes(out[i]) == hashlib.sha256(m).digest(), (length, i)

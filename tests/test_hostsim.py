@@ -237,3 +237,24 @@ def test_fp_sqr_dedicated():
         arr = np.array(hs.limbs(raw), dtype=np.uint32)
         got = call(lib.hs_fp_sqr, arr, out_words=12)
         assert sum(int(x) << (32 * i) for i, x in enumerate(got)) == raw * raw * hs.RINV % P
+
+
+def test_team_pairing_matches_oracle_and_serial():
+    """3-lane cooperative Miller loop + final exponentiation (csrc/team.cuh, three host threads) == oracle pairing."""
+    for a, b in ((1, 1), (5, 7), (rnd.randrange(R), rnd.randrange(R))):
+        pj, qj = E1.mul(G1, a), E2.mul(G2, b)
+        out = np.zeros(144, dtype=np.uint32)
+        assert lib.hs_team_pairing(hs.buf(g1_compress(pj)), hs.buf(g2_compress(qj)), hs.ptr(out), 1, 0) == 0
+        assert hs.fp12_v(out) == pairing(pj, qj)
+        assert lib.hs_team_pairing(hs.buf(g1_compress(pj)), hs.buf(g2_compress(qj)), hs.ptr(out), 1, 1) == 0
+        assert hs.fp12_v(out) == pairing(E1.mul(pj, 3), qj)
+        # Miller value alone must equal the serial device code bit for bit
+        o1, o2 = np.zeros(144, dtype=np.uint32), np.zeros(144, dtype=np.uint32)
+        lib.hs_team_pairing(hs.buf(g1_compress(pj)), hs.buf(g2_compress(qj)), hs.ptr(o1), 0, 1)
+        lib.hs_pairing(hs.buf(g1_compress(pj)), hs.buf(g2_compress(qj)), hs.ptr(o2), 0, 1)
+        assert np.array_equal(o1, o2)
+    f = rf12()
+    assert hs.fp12_v(call(lib.hs_team_final_exp, hs.fp12_m(f), out_words=144)) == final_exponentiation(f)
+    out = np.zeros(144, dtype=np.uint32)
+    lib.hs_team_pairing(hs.buf(g1_compress(G1)), hs.buf(bytes([0xC0]) + bytes(95)), hs.ptr(out), 1, 0)
+    assert hs.fp12_v(out) == F12_ONE
