@@ -35,6 +35,7 @@ SLOTS, COMMITTEES_PER_SLOT, COMMITTEE_SIZE = 32, 64, 512
 N_AGG = SLOTS * COMMITTEES_PER_SLOT
 N_BLOCKS = 10000
 R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+TRAFFIC_BYTES_K3 = 1.80e9      # dram read 0.15 GB + write 1.65 GB per launch (per-thread window tables in local memory), ncu r1 capture
 WORKLOAD = "full epoch: 32 slots x 64 committees x 512 members = 2^20 validators per rank; 10000-block fork tree"
 
 
@@ -359,6 +360,15 @@ def run_gpu(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         algo_bytes = 96 * N_VAL + 96 * N_AGG                              # bls.Aggregate = 96n + 96s
         achieved = algo_bytes / (ms_agg * 1e-3) / 1e9
+        # integer-pipe reading of the same launch: IMAD.WIDE.U32 instructions per signature, counted from the SASS of fp_sqr (222)
+        # and fp_mul (288): 2 exponentiations x (379 squarings + 84 multiplications) + ~60 multiplications for the curve
+        # equation, sign fix and the segment additions.  Peak = 32 wide MACs / clk / SM (one IMAD.WIDE per 4 cycles per scheduler,
+        # ncu: sm__pipe_fmaheavy) x SMs x the SM clock sampled during the timed region.
+        wide_per_sig = 2 * (379 * 222 + 84 * 288) + 60 * 288
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        int_peak = 32.0 * n_sm * sm_mhz * 1e6
+        int_ach = wide_per_sig * N_VAL / (ms_agg * 1e-3)
         line = {
             "metric": METRIC, "value": world * N_VAL / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev, "ms_per_step_unpipelined": ms_sync, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -372,8 +382,11 @@ def run_gpu(args):
             "get_head_p50_us": p50, "get_head_p99_us": p99, "head_index": head0,
             "stage_ms": {"bls_aggregate_2^20_sigs": ms_agg, "fast_aggregate_verify_2048": ms_verify},
             "roofline": {"bound": "hbm", "kernel": "bls.Aggregate (k_g2_decompress + k_g2_segment_sum)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "integer-pipe bound, not HBM bound: ~950 Fp mul (x ~290 IMAD.WIDE) per 96-byte signature; see DESIGN.md"},
+                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_K3, "peak_source": peak_src,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_g2_decompress (profiles/)",
+                         "note": "integer-pipe bound, not HBM bound (ncu: sm__pipe_fmaheavy_cycles_active 95%, DRAM 0.6% of peak); see int_pipe and DESIGN.md",
+                         "int_pipe": {"achieved": int_ach / 1e12, "peak": int_peak / 1e12, "unit": "T wide-MAC/s", "frac": int_ach / int_peak,
+                                      "wide_mac_per_signature": wide_per_sig}},
             "setup_s": W["setup_s"],
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -60,7 +60,7 @@ def _expected(pks, members, off, msgs, bits, sigs):
     return aggs, oks
 
 
-@pytest.mark.parametrize("mode", ["sync", "pipelined"])
+@pytest.mark.parametrize("mode", ["sync", "pipelined", "pipelined_host", "sync_host"])
 def test_epoch_pipeline_matches_oracle(mode):
     from pos_evolution_b200.engine import Engine
     from pos_evolution_b200.epoch import EpochProcessor
@@ -93,7 +93,18 @@ def test_epoch_pipeline_matches_oracle(mode):
              torch.as_tensor(bits, device=dev), torch.as_tensor(np.frombuffer(b"".join(msgs), dtype=np.uint8).reshape(-1, 32).copy(), device=dev),
              torch.as_tensor(te, device=dev), torch.as_tensor(bi, device=dev)]
         keep_alive.append(d)
-        if mode == "sync":
+        if mode in ("pipelined_host", "sync_host"):
+            h = [x.cpu().pin_memory() for x in d]
+            keep_alive.append(h)
+            if mode == "sync_host":
+                ok, hd = ep.process_epoch_host(*h)
+                tickets.append((ok.numpy().tolist(), hd, ep.d_agg_sig[0].cpu().numpy().copy()))
+            else:
+                t = ep.submit_host(*h)
+                if t is not None:
+                    ok, hd = t.wait()
+                    tickets.append((ok.numpy().tolist(), hd, ep.d_agg_sig[(k - 1) & 1].cpu().numpy().copy()))
+        elif mode == "sync":
             ok, hd = ep.process_epoch_dev(*d)
             torch.cuda.synchronize()
             tickets.append((ok.cpu().numpy().tolist(), int(hd.item()), ep.d_agg_sig[0].cpu().numpy().copy()))
@@ -103,7 +114,7 @@ def test_epoch_pipeline_matches_oracle(mode):
                 ok, hd = t.wait()
                 slot_prev = (k - 1) & 1
                 tickets.append((ok.cpu().numpy().tolist(), hd, ep.d_agg_sig[slot_prev].cpu().numpy().copy()))
-    if mode == "pipelined":
+    if mode in ("pipelined", "pipelined_host"):
         ok, hd = ep.drain().wait()
         tickets.append((ok.cpu().numpy().tolist(), hd, ep.d_agg_sig[(n_epochs - 1) & 1].cpu().numpy().copy()))
     assert len(tickets) == n_epochs
