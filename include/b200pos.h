@@ -89,6 +89,11 @@ int b2_hash_to_g2(b2_ctx* ctx, const uint8_t* msg32, uint32_t n_msg, uint8_t* ou
 /* `hash` of the spec (SHA-256; pos-evolution.md:486, :522, :525), batched over n messages of msg_len bytes each */
 int b2_sha256_batch(b2_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint64_t n, uint8_t* out32);
 
+/* compute_signing_root(AttestationData, domain) (pattern of pos-evolution.md:163; containers :689-697, :219-221) for n attestations:
+ * data128 = the 128-byte SSZ serialisation of each AttestationData; domain32 = one 32-byte domain for the batch, or one per
+ * attestation when per_attestation_domain != 0.  SSZ merkleization (10 SHA-256 per attestation) runs on the GPU. */
+int b2_signing_roots(b2_ctx* ctx, const uint8_t* data128, const uint8_t* domain32, int per_attestation_domain, uint32_t n, uint8_t* out32);
+
 /* ---- committees: compute_committee / compute_shuffled_index (pos-evolution.md:495-534) for a whole epoch.
  * members_out[i] = active[compute_shuffled_index(i, n_active, seed)] (active == NULL: identity), so committee k of
  * `count` is members_out[n*k/count .. n*(k+1)/count).  SHA-256 and the swap-or-not rounds run on the GPU. */

@@ -38,6 +38,7 @@ SIGNATURES = {
     "b2_sign": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p]),
     "b2_hash_to_g2": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p]),
     "b2_sha256_batch": (c_int, [c_void_p, c_void_p, c_uint32, c_uint64, c_void_p]),
+    "b2_signing_roots": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_void_p]),
     "b2_shuffle_committees": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_void_p]),
     "b2_shuffle_committees_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_void_p, c_void_p]),
     "b2_latest_messages_reset": (c_int, [c_void_p]),

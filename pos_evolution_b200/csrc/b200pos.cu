@@ -42,9 +42,8 @@ struct b2_ctx {
     uint8_t* d_equiv = nullptr;
     // block tree
     uint32_t n_blocks = 0;
-    uint32_t *d_pre = nullptr, *d_size = nullptr, *d_child_off = nullptr, *d_child_idx = nullptr, *d_rank = nullptr, *d_next = nullptr;
-    uint8_t* d_keep = nullptr;
-    unsigned long long *d_votes = nullptr, *d_prefix = nullptr, *d_weight = nullptr;
+    uint32_t *d_pre = nullptr, *d_inv = nullptr, *d_size_keep = nullptr, *d_rank = nullptr, *d_next = nullptr, *d_gsize = nullptr;
+    unsigned long long *d_votes = nullptr, *d_prefix = nullptr, *d_weight = nullptr, *d_w2 = nullptr;
     uint32_t* d_head = nullptr;
     // scratch
     dbuf sc_pkjac, sc_pkst, sc_haff, sc_hflag, sc_g2aff, sc_g2st, sc_rec, sc_val;
@@ -125,7 +124,7 @@ int b2_init(int device, b2_ctx** out) {
         cudaEvent_t* evs[4] = {&ctx->slot[i].ev_join0, &ctx->slot[i].ev_join1, &ctx->slot[i].ev_seg, &ctx->slot[i].ev_tail_done};
         for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(evs[k], cudaEventDisableTiming);
     }
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_votes_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     ctx->n_sm = prop.multiProcessorCount;
     if (e != cudaSuccess) {
@@ -141,7 +140,7 @@ void b2_destroy(b2_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* ptrs[] = {ctx->d_records, ctx->d_valid, ctx->d_eff, ctx->d_flags, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_pre,
-                    ctx->d_size, ctx->d_child_off, ctx->d_child_idx, ctx->d_rank, ctx->d_next, ctx->d_keep, ctx->d_votes, ctx->d_prefix,
+                    ctx->d_inv, ctx->d_size_keep, ctx->d_gsize, ctx->d_w2, ctx->d_rank, ctx->d_next, ctx->d_votes, ctx->d_prefix,
                     ctx->d_weight, ctx->d_head};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -603,6 +602,24 @@ int b2_sha256_batch(b2_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint64_t
     return B2_OK;
 }
 
+// ------------------------------------------------------------------------------------------ SSZ signing roots
+int b2_signing_roots(b2_ctx* ctx, const uint8_t* data128, const uint8_t* domain32, int per_attestation_domain, uint32_t n, uint8_t* out32) {
+    REQUIRE(ctx && data128 && domain32 && out32 && n > 0, "signing_roots: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    const size_t dom_bytes = per_attestation_domain ? (size_t)n * 32 : 32;
+    if ((rc = ensure(ctx, ctx->in_a, (size_t)n * 128)) || (rc = ensure(ctx, ctx->in_e, dom_bytes)) || (rc = ensure(ctx, ctx->out_a, (size_t)n * 32))) return rc;
+    CK(cudaMemcpyAsync(ctx->in_a.p, data128, (size_t)n * 128, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_e.p, domain32, dom_bytes, cudaMemcpyHostToDevice, s));
+    k_signing_roots<<<blocks_for(n, 64), 64, 0, s>>>((const uint8_t*)ctx->in_a.p, (const uint8_t*)ctx->in_e.p, per_attestation_domain ? 32u : 0u, n,
+                                                    (uint8_t*)ctx->out_a.p);
+    CKL(ctx);
+    CK(cudaMemcpyAsync(out32, ctx->out_a.p, (size_t)n * 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------------------------------ committee shuffle
 int b2_shuffle_committees_dev(b2_ctx* ctx, const uint8_t* d_seed32, const uint32_t* d_active, uint32_t n_active, uint32_t rounds,
                               uint32_t* d_members_out, void* stream) {
@@ -760,18 +777,24 @@ int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, cons
     for (uint32_t i = 0; i < n; i++) rank[order[i]] = i;
     CK(cudaSetDevice(ctx->device));
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_pre, n)) || (rc = dev_alloc(ctx, &ctx->d_size, n)) || (rc = dev_alloc(ctx, &ctx->d_child_off, (size_t)n + 1)) ||
-        (rc = dev_alloc(ctx, &ctx->d_child_idx, n)) || (rc = dev_alloc(ctx, &ctx->d_rank, n)) || (rc = dev_alloc(ctx, &ctx->d_next, n)) ||
-        (rc = dev_alloc(ctx, &ctx->d_keep, n)) || (rc = dev_alloc(ctx, &ctx->d_votes, n)) || (rc = dev_alloc(ctx, &ctx->d_prefix, (size_t)n + 1)) ||
+    // everything the tree kernel reads is stored in pre-order
+    std::vector<uint32_t> inv(n), size_keep(n), rank_p(n);
+    for (uint32_t b = 0; b < n; b++) {
+        const uint32_t p = pre[b];
+        inv[p] = b;
+        size_keep[p] = size[b] | (keep[b] ? 0x80000000u : 0u);
+        rank_p[p] = rank[b];
+    }
+    if ((rc = dev_alloc(ctx, &ctx->d_pre, n)) || (rc = dev_alloc(ctx, &ctx->d_inv, n)) || (rc = dev_alloc(ctx, &ctx->d_size_keep, n)) ||
+        (rc = dev_alloc(ctx, &ctx->d_rank, n)) || (rc = dev_alloc(ctx, &ctx->d_next, n)) || (rc = dev_alloc(ctx, &ctx->d_gsize, n)) ||
+        (rc = dev_alloc(ctx, &ctx->d_votes, n)) || (rc = dev_alloc(ctx, &ctx->d_prefix, (size_t)n + 1)) || (rc = dev_alloc(ctx, &ctx->d_w2, n)) ||
         (rc = dev_alloc(ctx, &ctx->d_weight, n)) || (rc = dev_alloc(ctx, &ctx->d_head, 1)))
         return rc;
     cudaStream_t s = ctx->s_main;
     CK(cudaMemcpyAsync(ctx->d_pre, pre.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_size, size.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_child_off, child_off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
-    if (n > 1) CK(cudaMemcpyAsync(ctx->d_child_idx, child_idx.data(), (size_t)(n - 1) * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_rank, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_keep, keep.data(), n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_inv, inv.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_size_keep, size_keep.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_rank, rank_p.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(ctx->d_votes, 0, (size_t)n * 8, s));
     CK(cudaStreamSynchronize(s));
     ctx->n_blocks = n;
@@ -806,21 +829,21 @@ int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t jus
     ghost_tree_args A;
     A.n = ctx->n_blocks;
     A.pre = ctx->d_pre;
-    A.size = ctx->d_size;
-    A.child_off = ctx->d_child_off;
-    A.child_idx = ctx->d_child_idx;
+    A.inv = ctx->d_inv;
+    A.size_keep = ctx->d_size_keep;
     A.rank = ctx->d_rank;
-    A.keep = ctx->d_keep;
     A.votes = (unsigned long long*)d_votes_preorder;
-    A.prefix = ctx->d_prefix;
-    A.next = ctx->d_next;
+    A.g_w = ctx->d_prefix;
+    A.g_w2 = ctx->d_w2;
+    A.g_size = ctx->d_gsize;
+    A.g_next = ctx->d_next;
     A.weight_out = (unsigned long long*)d_weight_out;
     A.head_out = d_head_idx_out;
     A.justified = justified_idx;
     A.boost_idx = boost_idx;
     A.boost_score = boost_score;
-    size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 4;
-    A.use_smem = smem <= 200 * 1024;
+    size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8;
+    A.use_smem = smem <= 227 * 1024 && A.n <= 15 * 1024;
     k_ghost_tree<<<1, 1024, A.use_smem ? smem : 0, s>>>(A);
     CKL(ctx);
     return B2_OK;

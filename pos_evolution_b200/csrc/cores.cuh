@@ -159,4 +159,36 @@ HD uint8_t core_final_verdict(const fp12& f0, const fp12& f1, uint8_t pk_status,
     return fp12_is_one(final_exponentiation(fp12_mul(f0, f1))) ? 1 : 0;
 }
 
+// ---- SSZ: compute_signing_root(AttestationData, domain) (see k_signing_roots in kernels.cuh)
+HD void sha256_pair(const uint8_t* left32, const uint8_t* right32, uint8_t* out32) {
+    sha256_ctx c;
+    sha256_init(c);
+    sha256_update(c, left32, 32);
+    sha256_update(c, right32, 32);
+    sha256_final(c, out32);
+}
+HD void attestation_signing_root(const uint8_t* data128, const uint8_t* domain32, uint8_t* out32) {
+    uint8_t chunk[8][32];
+#pragma unroll 1
+    for (int i = 0; i < 8; i++)
+        for (int k = 0; k < 32; k++) chunk[i][k] = 0;
+    uint8_t ep[32];
+    for (int k = 0; k < 8; k++) {
+        chunk[0][k] = data128[k];            // slot
+        chunk[1][k] = data128[8 + k];        // index
+    }
+    for (int k = 0; k < 32; k++) chunk[2][k] = data128[16 + k];
+    for (int k = 0; k < 32; k++) ep[k] = k < 8 ? data128[48 + k] : 0;
+    sha256_pair(ep, data128 + 56, chunk[3]);     // htr(source)
+    for (int k = 0; k < 32; k++) ep[k] = k < 8 ? data128[88 + k] : 0;
+    sha256_pair(ep, data128 + 96, chunk[4]);     // htr(target)
+    uint8_t l1[4][32], l2[2][32], root[32];
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) sha256_pair(chunk[2 * i], chunk[2 * i + 1], l1[i]);
+    sha256_pair(l1[0], l1[1], l2[0]);
+    sha256_pair(l1[2], l1[3], l2[1]);
+    sha256_pair(l2[0], l2[1], root);
+    sha256_pair(root, domain32, out32);
+}
+
 }  // namespace b2

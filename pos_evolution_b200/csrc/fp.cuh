@@ -207,9 +207,10 @@ HD fp fp_sqr(const fp& a) {
     t[0] = add_cc(ue[0], uo[0]);
 #pragma unroll
     for (int k = 1; k < 24; k++) t[k] = addc_cc(ue[k], uo[k]);
-    t[0] = add_cc(t[0], t[0]);
+    // doubling by funnel shifts (24 independent ops instead of a 24-long carry chain); the sum is < 2^767, nothing is shifted out
 #pragma unroll
-    for (int k = 1; k < 24; k++) t[k] = addc_cc(t[k], t[k]);
+    for (int k = 23; k >= 1; k--) t[k] = (t[k] << 1) | (t[k - 1] >> 31);
+    t[0] <<= 1;
 #pragma unroll
     for (int i = 0; i < 12; i++) mul_wide(d[2 * i], d[2 * i + 1], a.l[i], a.l[i]);
     t[0] = add_cc(t[0], d[0]);

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(128) k_g1_segment_sum(const uint32_t* __restri
 
 // ------------------------------------------------------------------------------------------ K3: bls.Aggregate
 // stage 1: one thread per signature: ZCash decode + Fp2 square root (two Fp exponentiations) -> affine point
-__global__ void __launch_bounds__(128) k_g2_decompress(const uint8_t* __restrict__ sig96, uint64_t n, uint32_t* aff_out, uint8_t* st_out) {
+__global__ void __launch_bounds__(128, 4) k_g2_decompress(const uint8_t* __restrict__ sig96, uint64_t n, uint32_t* aff_out, uint8_t* st_out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2_aff s;
@@ -464,24 +464,26 @@ __global__ void __launch_bounds__(1024) k_ghost_votes_smem(uint64_t n, const uns
 }
 
 // ------------------------------------------------------------------------------------------ K9: subtree weights + head
-// Single block.  Blocks were renumbered in DFS pre-order at b2_tree_load, so the subtree of b is the
-// contiguous range [pre[b], pre[b]+size[b]) and get_latest_attesting_balance(b) is a difference of two
-// prefix sums of the direct votes (+ proposer boost on one block).  The head walk of get_head
-// (argmax over children of (weight, root), repeated to a leaf) is done for all blocks at once:
-// best_child[], then pointer jumping (log2(depth) rounds) from the justified root.
-// Scratch arrays live in shared memory when they fit, else in global memory.
+// Single block.  b2_tree_load renumbers the blocks in DFS pre-order and stores every per-block array in that order, so
+//   * the subtree of the block at position p is the contiguous range [p, p + size[p]) and its
+//     get_latest_attesting_balance is a difference of two prefix sums of the direct votes (+ boost on one block);
+//   * the children of p are p+1, p+1+size[p+1], ... -- no child lists;
+//   * all loads are coalesced and everything the head walk touches lives in shared memory (16 B per block).
+// The head walk of get_head (argmax over children of (weight, root), repeated down to a leaf) is done for all blocks at
+// once: best_child[], then pointer jumping (ceil(log2 n) rounds) from the justified root.  Trees too large for shared
+// memory (> ~14 000 blocks) use the same code on global scratch.
 struct ghost_tree_args {
     uint32_t n;
-    const uint32_t* pre;        // block -> pre-order position
-    const uint32_t* size;       // subtree size
-    const uint32_t* child_off;  // CSR children (block indices)
-    const uint32_t* child_idx;
-    const uint32_t* rank;       // lexicographic rank of the 32-byte root
-    const uint8_t* keep;        // get_filtered_block_tree membership
-    unsigned long long* votes;  // in: direct votes in pre-order; zeroed on exit
-    unsigned long long* prefix; // scratch n+1 (global fallback)
-    uint32_t* next;             // scratch n   (global fallback)
-    unsigned long long* weight_out;  // optional, per block
+    const uint32_t* pre;         // block -> pre-order position
+    const uint32_t* inv;         // pre-order position -> block
+    const uint32_t* size_keep;   // pre-order: subtree size | (get_filtered_block_tree membership << 31)
+    const uint32_t* rank;        // pre-order: lexicographic rank of the 32-byte root (tie-break of :1114-1116)
+    unsigned long long* votes;   // in: direct votes in pre-order; zeroed on exit
+    unsigned long long* g_w;     // global fallback scratch n+1 (prefix sums)
+    unsigned long long* g_w2;    // global fallback scratch n (weights)
+    uint32_t* g_size;            // global fallback scratch n
+    uint32_t* g_next;            // global fallback scratch n
+    unsigned long long* weight_out;  // optional, per block (original numbering)
     uint32_t* head_out;
     uint32_t justified;
     int32_t boost_idx;
@@ -492,15 +494,24 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
     extern __shared__ unsigned long long smem_u64[];
     __shared__ unsigned long long warp_tot[32];
     const uint32_t n = A.n, tid = threadIdx.x, T = blockDim.x;
-    unsigned long long* S = A.use_smem ? smem_u64 : A.prefix;
-    uint32_t* next = A.use_smem ? reinterpret_cast<uint32_t*>(smem_u64 + (n + 1)) : A.next;
-    if (tid == 0 && A.boost_idx >= 0) A.votes[A.pre[A.boost_idx]] += A.boost_score;
+    unsigned long long* W = A.use_smem ? smem_u64 : A.g_w;                                     // n+1: votes -> prefix -> weights
+    uint32_t* size = A.use_smem ? reinterpret_cast<uint32_t*>(smem_u64 + (n + 1)) : A.g_size;   // n
+    uint32_t* next = A.use_smem ? size + n : A.g_next;                                          // n
+    const uint32_t boost_p = A.boost_idx >= 0 ? A.pre[A.boost_idx] : 0xffffffffu;
+    // stage votes (+ boost) and sizes, coalesced; leave the global accumulator clean for the next call
+    for (uint32_t p = tid; p < n; p += T) {
+        unsigned long long v = A.votes[p];
+        A.votes[p] = 0;
+        if (p == boost_p) v += A.boost_score;
+        W[p] = v;
+        size[p] = A.size_keep[p];
+    }
     __syncthreads();
-    // exclusive prefix sum of votes[0..n) -> S[0..n]
+    // exclusive prefix sum over W[0..n): thread t owns the contiguous chunk [lo, hi)
     const uint32_t per = (n + T - 1) / T;
     const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
     unsigned long long local = 0;
-    for (uint32_t i = lo; i < hi; i++) local += A.votes[i];
+    for (uint32_t i = lo; i < hi; i++) local += W[i];
     unsigned long long incl = local;
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -517,56 +528,73 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
             unsigned long long o = __shfl_up_sync(B2_FULL_MASK, wi, d);
             if (lane >= d) wi += o;
         }
-        warp_tot[lane] = wi - w;                 // exclusive offset of each warp
+        warp_tot[lane] = wi - w;
     }
     __syncthreads();
     unsigned long long run = warp_tot[warp] + incl - local;
     for (uint32_t i = lo; i < hi; i++) {
-        S[i] = run;
-        run += A.votes[i];
-        A.votes[i] = 0;                          // leave the accumulator clean for the next call
+        unsigned long long v = W[i];
+        W[i] = run;
+        run += v;
     }
-    if (hi == n && lo < n) S[n] = run;
-    if (n == 0 && tid == 0) S[0] = 0;
+    if (lo < n && hi == n) W[n] = run;
+    if (n == 0 && tid == 0) W[0] = 0;
     __syncthreads();
-    // weights and best child
-    for (uint32_t b = tid; b < n; b += T) {
-        uint32_t p = A.pre[b];
-        if (A.weight_out) A.weight_out[b] = S[p + A.size[b]] - S[p];
-        uint32_t best = b;
-        unsigned long long bw = 0;
-        uint32_t br = 0;
-        bool have = false;
-        if (A.keep[b]) {
-            for (uint32_t k = A.child_off[b]; k < A.child_off[b + 1]; k++) {
-                uint32_t c = A.child_idx[k];
-                if (!A.keep[c]) continue;
-                uint32_t pc = A.pre[c];
-                unsigned long long w = S[pc + A.size[c]] - S[pc];
-                uint32_t r = A.rank[c];
-                if (!have || w > bw || (w == bw && r > br)) {
+    // weights: w[p] = S[p + size] - S[p].  Shared-memory mode overwrites S in place (through registers: the smem budget
+    // caps n at ~14 500 = 15 per thread); global mode writes a separate array.
+    unsigned long long* Wt = A.use_smem ? W : A.g_w2;
+    if (A.use_smem) {
+        constexpr int MAXPT = 15;
+        unsigned long long wreg[MAXPT];
+#pragma unroll
+        for (int j = 0; j < MAXPT; j++) {
+            uint32_t p = tid + j * T;
+            if (p < n) wreg[j] = W[p + (size[p] & 0x7fffffffu)] - W[p];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < MAXPT; j++) {
+            uint32_t p = tid + j * T;
+            if (p < n) W[p] = wreg[j];
+        }
+    } else {
+        for (uint32_t p = tid; p < n; p += T) Wt[p] = W[p + (size[p] & 0x7fffffffu)] - W[p];
+    }
+    __syncthreads();
+    if (A.weight_out)
+        for (uint32_t b = tid; b < n; b += T) A.weight_out[b] = Wt[A.pre[b]];
+    // best child of every kept block
+    for (uint32_t p = tid; p < n; p += T) {
+        const uint32_t sk = size[p];
+        uint32_t best = p;
+        if (sk >> 31) {
+            const uint32_t end = p + (sk & 0x7fffffffu);
+            unsigned long long bw = 0;
+            bool have = false;
+            for (uint32_t c = p + 1; c < end; c += size[c] & 0x7fffffffu) {
+                if (!(size[c] >> 31)) continue;
+                const unsigned long long w = Wt[c];
+                if (!have || w > bw || (w == bw && A.rank[c] > A.rank[best])) {
                     have = true;
                     best = c;
                     bw = w;
-                    br = r;
                 }
             }
         }
-        next[b] = best;
+        next[p] = best;
     }
     __syncthreads();
-    // pointer jumping: after k rounds next[b] is at least 2^k steps down b's best path (or its leaf).
-    // Updated in place: a racing reader sees either the old or the new hop target of another block; both lie
-    // on the same best path, the hop distance still at least doubles per round, and the fix point is the leaf.
+    // pointer jumping, in place: a racing reader sees the old or the new hop target of another block; both lie on the same
+    // best path, the hop distance at least doubles per round, and the fix point is the leaf
     volatile uint32_t* vn = next;
     for (uint32_t span = 1; span < n; span <<= 1) {
-        for (uint32_t b = tid; b < n; b += T) {
-            uint32_t t2 = vn[vn[b]];
-            vn[b] = t2;
+        for (uint32_t p = tid; p < n; p += T) {
+            uint32_t t2 = vn[vn[p]];
+            vn[p] = t2;
         }
         __syncthreads();
     }
-    if (tid == 0) *A.head_out = (A.justified < n) ? next[A.justified] : 0xffffffffu;
+    if (tid == 0) *A.head_out = (A.justified < n) ? A.inv[next[A.pre[A.justified]]] : 0xffffffffu;
 }
 
 }  // namespace b2
@@ -665,3 +693,23 @@ __global__ void __launch_bounds__(128) k_sha256_fixed(const uint8_t* __restrict_
 }  // namespace b2
 static_assert(B2_TEAMS_PER_WARP * 3 <= 32, "a warp holds at most 10 three-lane teams");
 static_assert(B2_TEAMS_PER_WARP * sizeof(b2::team_ws) <= 48 * 1024, "team workspaces must fit the default dynamic shared memory limit");
+
+// ------------------------------------------------------------------------------------------ SSZ signing roots on the device
+// compute_signing_root(AttestationData, domain) (pattern of /root/reference/pos-evolution.md:163; containers :689-697, :219-221):
+//   hash_tree_root(AttestationData) = Merkle root of 8 chunks [slot, index, beacon_block_root, htr(source), htr(target), 0, 0, 0],
+//   htr(Checkpoint) = SHA256(pad32(LE64(epoch)) || root), signing root = SHA256(object_root || domain).
+// Input record = the 128-byte SSZ serialisation of AttestationData (slot u64, index u64, beacon_block_root, source.epoch u64,
+// source.root, target.epoch u64, target.root).  One thread per attestation, 10 two-block SHA-256 evaluations.
+namespace b2 {
+// domain_stride = 0: one domain for the whole batch; 32: one per attestation
+__global__ void __launch_bounds__(64) k_signing_roots(const uint8_t* __restrict__ data128, const uint8_t* __restrict__ domain32, uint32_t domain_stride,
+                                                       uint32_t n, uint8_t* out32) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t d[128], dom[32], o[32];
+    for (int k = 0; k < 128; k++) d[k] = data128[128 * (uint64_t)i + k];
+    for (int k = 0; k < 32; k++) dom[k] = domain32[(uint64_t)i * domain_stride + k];
+    attestation_signing_root(d, dom, o);
+    for (int k = 0; k < 32; k++) out32[32 * (uint64_t)i + k] = o[k];
+}
+}  // namespace b2

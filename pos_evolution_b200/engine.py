@@ -158,6 +158,16 @@ class Engine:
         self._ck(self.lib.b2_sha256_batch(self.h, _p(m) if msg_len else None, msg_len, n, _p(out)))
         return out
 
+    def signing_roots(self, data128, domains32):
+        """compute_signing_root for n attestations: data128 uint8[n,128] (SSZ-serialised AttestationData), domains32 uint8[32] or uint8[n,32]."""
+        d = _c(data128, np.uint8).reshape(-1, 128)
+        dom = _c(domains32, np.uint8).reshape(-1, 32)
+        n = d.shape[0]
+        assert dom.shape[0] in (1, n)
+        out = np.zeros((n, 32), dtype=np.uint8)
+        self._ck(self.lib.b2_signing_roots(self.h, _p(d), _p(dom), 1 if dom.shape[0] == n and n > 1 else 0, n, _p(out)))
+        return out
+
     def shuffle_committees(self, seed32: bytes, n_active: int, rounds: int, active=None):
         """members[i] = active[compute_shuffled_index(i, n_active, seed)] for the whole active set, on the GPU."""
         seed = np.frombuffer(bytes(seed32), dtype=np.uint8)

@@ -168,6 +168,12 @@ def hash_tree_root_attestation_data(d: AttestationData) -> bytes:
                     hash_tree_root_checkpoint(d.source), hash_tree_root_checkpoint(d.target)])
 
 
+def serialize_attestation_data(d: AttestationData) -> bytes:
+    """SSZ serialisation of the fixed-size container (128 bytes): the record format of Engine.signing_roots."""
+    return (int(d.slot).to_bytes(8, "little") + int(d.index).to_bytes(8, "little") + bytes(d.beacon_block_root)
+            + int(d.source.epoch).to_bytes(8, "little") + bytes(d.source.root) + int(d.target.epoch).to_bytes(8, "little") + bytes(d.target.root))
+
+
 def compute_domain(domain_type: bytes, fork_version: bytes, genesis_validators_root: bytes) -> bytes:
     fork_data_root = _merkle([bytes(fork_version) + bytes(28), bytes(genesis_validators_root)])
     return bytes(domain_type) + fork_data_root[:28]
@@ -370,16 +376,20 @@ class Spec:
             return np.zeros(0, dtype=np.uint8)
         self.sync_registry(state)
         n = len(state.validators)
-        members, off, msgs, sigs, structurally_ok = [], [0], [], [], []
+        members, off, sigs, structurally_ok, data128, domains = [], [0], [], [], [], []
         for ia in indexed_list:
             idx = list(ia.attesting_indices)
             good = len(idx) > 0 and idx == sorted(set(idx)) and idx[-1] < n and len(bytes(ia.signature)) == 96
             structurally_ok.append(good)
             members += idx if good else []
             off.append(len(members))
-            domain = self.get_domain(state, DOMAIN_BEACON_ATTESTER, ia.data.target.epoch)
-            msgs.append(self.compute_signing_root(ia.data, domain))
+            domains.append(self.get_domain(state, DOMAIN_BEACON_ATTESTER, ia.data.target.epoch))
+            data128.append(serialize_attestation_data(ia.data))
             sigs.append(bytes(ia.signature) if len(bytes(ia.signature)) == 96 else bytes(96))
+        if hasattr(self.engine, "signing_roots"):           # SSZ merkleization on the GPU (k_signing_roots)
+            msgs_arr = self.engine.signing_roots(np.frombuffer(b"".join(data128), dtype=np.uint8), np.frombuffer(b"".join(domains), dtype=np.uint8))
+        else:
+            msgs_arr = np.frombuffer(b"".join(self.compute_signing_root(ia.data, dom) for ia, dom in zip(indexed_list, domains)), dtype=np.uint8)
         sizes = np.diff(np.asarray(off, dtype=np.int64))
         stride = max(1, (int(sizes.max()) + 7) // 8)
         bits = np.zeros((len(indexed_list), stride), dtype=np.uint8)
@@ -389,8 +399,7 @@ class Spec:
             if rem:
                 bits[a, full] = (1 << rem) - 1
         ok = self.engine.fast_aggregate_verify(np.asarray(members, dtype=np.uint32), off, bits,
-                                               np.frombuffer(b"".join(msgs), dtype=np.uint8),
-                                               np.frombuffer(b"".join(sigs), dtype=np.uint8))
+                                               msgs_arr, np.frombuffer(b"".join(sigs), dtype=np.uint8))
         return ok & np.asarray(structurally_ok, dtype=np.uint8)
 
     # ------------------------------------------------------------------ participation helpers (called at :733, :747-754)

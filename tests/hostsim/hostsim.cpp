@@ -235,3 +235,5 @@ extern "C" void hs_team_final_exp(const uint32_t* in, uint32_t* out) {
     pthread_barrier_destroy(&bar);
     delete ws;
 }
+
+extern "C" void hs_signing_root(const uint8_t* data128, const uint8_t* domain32, uint8_t* out32) { attestation_signing_root(data128, domain32, out32); }

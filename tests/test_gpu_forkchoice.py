@@ -25,7 +25,7 @@ def _registry(eng, n, eff, active):
     eng.registry_load(pk, eff, active)
 
 
-@pytest.mark.parametrize("n_val,n_blk,seed", [(64, 1, 1), (64, 2, 2), (1000, 50, 3), (5000, 300, 4), (1 << 20, 10000, 4)])
+@pytest.mark.parametrize("n_val,n_blk,seed", [(64, 1, 1), (64, 2, 2), (1000, 50, 3), (5000, 300, 4), (1 << 20, 10000, 4), (3000, 14000, 6), (3000, 20000, 7)])
 def test_weights_and_head(eng, n_val, n_blk, seed):
     parent, slot, roots, leaf_viable = scenarios.fork_tree(n_blk, seed)
     msg_block, has_msg, equiv, active, eff = scenarios.votes(n_val, n_blk, seed)
@@ -112,3 +112,26 @@ def test_gpu_sha256_batch(eng, length):
     for i in range(n):
         m = bytes(msgs[i]) if length else b""
         assert bytes(out[i]) == hashlib.sha256(m).digest(), (length, i)
+
+
+def test_gpu_signing_roots_match_oracle(eng):
+    from oracle import spec as OS
+    from oracle.ssz import compute_domain
+    rng = np.random.default_rng(8)
+    n = 300
+    datas, doms, ser = [], [], []
+    for i in range(n):
+        d = OS.AttestationData(int(rng.integers(0, 2**62)), int(rng.integers(0, 64)), bytes(rng.integers(0, 256, 32, dtype=np.uint8)),
+                               OS.Checkpoint(int(rng.integers(0, 2**40)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))),
+                               OS.Checkpoint(int(rng.integers(0, 2**40)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))))
+        dom = compute_domain(OS.DOMAIN_BEACON_ATTESTER, bytes(rng.integers(0, 256, 4, dtype=np.uint8)), bytes(rng.integers(0, 256, 32, dtype=np.uint8)))
+        datas.append(d)
+        doms.append(dom)
+        ser.append(d.slot.to_bytes(8, "little") + d.index.to_bytes(8, "little") + d.beacon_block_root + d.source.epoch.to_bytes(8, "little")
+                   + d.source.root + d.target.epoch.to_bytes(8, "little") + d.target.root)
+    out = eng.signing_roots(np.frombuffer(b"".join(ser), dtype=np.uint8), np.frombuffer(b"".join(doms), dtype=np.uint8))
+    for i in range(n):
+        assert bytes(out[i]) == OS.Spec.compute_signing_root(datas[i], doms[i])
+    one = eng.signing_roots(np.frombuffer(b"".join(ser), dtype=np.uint8), np.frombuffer(doms[0], dtype=np.uint8))
+    for i in range(n):
+        assert bytes(one[i]) == OS.Spec.compute_signing_root(datas[i], doms[0])

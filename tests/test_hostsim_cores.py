@@ -80,3 +80,20 @@ def test_g2_aggregate_core():
     assert out.raw[:96] == B.Aggregate(sigs)
     assert out.raw[96:192] == sigs[2]
     assert out.raw[288:384] == sigs[0]
+
+
+def test_signing_root_core_matches_oracle():
+    from oracle import spec as OS
+    from oracle.ssz import compute_domain
+    rng = np.random.default_rng(2)
+    for _ in range(5):
+        d = OS.AttestationData(int(rng.integers(0, 2**62)), int(rng.integers(0, 64)), bytes(rng.integers(0, 256, 32, dtype=np.uint8)),
+                               OS.Checkpoint(int(rng.integers(0, 2**40)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))),
+                               OS.Checkpoint(int(rng.integers(0, 2**40)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))))
+        dom = compute_domain(OS.DOMAIN_BEACON_ATTESTER, b"\x00\x00\x00\x01", bytes(rng.integers(0, 256, 32, dtype=np.uint8)))
+        ser = (d.slot.to_bytes(8, "little") + d.index.to_bytes(8, "little") + d.beacon_block_root + d.source.epoch.to_bytes(8, "little") + d.source.root
+               + d.target.epoch.to_bytes(8, "little") + d.target.root)
+        assert len(ser) == 128
+        out = ctypes.create_string_buffer(32)
+        lib.hs_signing_root(hs.buf(ser), hs.buf(dom), out)
+        assert out.raw == OS.Spec.compute_signing_root(d, dom)
