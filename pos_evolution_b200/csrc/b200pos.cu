@@ -124,7 +124,7 @@ int b2_init(int device, b2_ctx** out) {
         cudaEvent_t* evs[4] = {&ctx->slot[i].ev_join0, &ctx->slot[i].ev_join1, &ctx->slot[i].ev_seg, &ctx->slot[i].ev_tail_done};
         for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(evs[k], cudaEventDisableTiming);
     }
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_votes_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     ctx->n_sm = prop.multiProcessorCount;
     if (e != cudaSuccess) {
@@ -843,7 +843,7 @@ int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t jus
     A.boost_idx = boost_idx;
     A.boost_score = boost_score;
     size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8;
-    A.use_smem = smem <= 227 * 1024 && A.n <= 15 * 1024;
+    A.use_smem = smem <= 226 * 1024 && A.n <= 15 * 1024;   // 227 KB per block minus the kernel's static shared memory
     k_ghost_tree<<<1, 1024, A.use_smem ? smem : 0, s>>>(A);
     CKL(ctx);
     return B2_OK;
