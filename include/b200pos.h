@@ -115,6 +115,17 @@ int b2_latest_messages_read(b2_ctx* ctx, uint64_t* epoch, uint32_t* block_idx, u
 int b2_latest_messages_update(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
                               const uint64_t* target_epoch, const uint32_t* block_idx, const uint8_t* accept, uint32_t n_agg);
 
+/* ---- participation flags and proposer-reward numerators: the bookkeeping loop of process_attestation (pos-evolution.md:738-754).
+ * `which`: 0 = state.current_epoch_participation, 1 = previous.  For a batch of attestations in list order, each accepted
+ * attestation a sets, for every selected member, the flags of flag_mask[a] (bit f = participation flag index f) that are not set
+ * yet, and numerator_out[a] receives sum get_base_reward(index) * PARTICIPATION_FLAG_WEIGHTS[f] over the flags IT set
+ * (get_base_reward = effective_balance / increment * base_reward_per_increment).  Order-exact for the whole batch. */
+int b2_participation_load(b2_ctx* ctx, int which, const uint8_t* participation, uint64_t n_validators);
+int b2_participation_read(b2_ctx* ctx, int which, uint8_t* participation_out, uint64_t n_validators);
+int b2_participation_update(b2_ctx* ctx, int which, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
+                            const uint8_t* flag_mask, const uint8_t* accept, uint32_t n_agg, uint64_t effective_balance_increment,
+                            uint64_t base_reward_per_increment, uint64_t* numerator_out);
+
 /* Store.blocks (pos-evolution.md:898) as arrays in topological order (parent[b] < b, parent[0] ignored; block 0 =
  * store.justified_checkpoint.root).  leaf_viable[b]: the get_filtered_block_tree leaf test (:1104, prose :1121-1124). */
 int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, const uint8_t* root32, const uint8_t* leaf_viable,

@@ -40,6 +40,9 @@ struct b2_ctx {
     unsigned long long* d_lmd_key = nullptr;
     uint32_t* d_lmd_block = nullptr;
     uint8_t* d_equiv = nullptr;
+    // epoch participation flags (0 = current, 1 = previous) and the per-(validator, flag) election table
+    uint32_t* d_part[2] = {nullptr, nullptr};
+    uint32_t* d_part_first = nullptr;
     // block tree
     uint32_t n_blocks = 0;
     uint32_t *d_pre = nullptr, *d_inv = nullptr, *d_size_keep = nullptr, *d_rank = nullptr, *d_next = nullptr, *d_gsize = nullptr;
@@ -139,7 +142,7 @@ void b2_destroy(b2_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {ctx->d_records, ctx->d_valid, ctx->d_eff, ctx->d_flags, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_pre,
+    void* ptrs[] = {ctx->d_part[0], ctx->d_part[1], ctx->d_part_first, ctx->d_records, ctx->d_valid, ctx->d_eff, ctx->d_flags, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_pre,
                     ctx->d_inv, ctx->d_size_keep, ctx->d_gsize, ctx->d_w2, ctx->d_rank, ctx->d_next, ctx->d_votes, ctx->d_prefix,
                     ctx->d_weight, ctx->d_head};
     for (void* p : ptrs)
@@ -197,6 +200,15 @@ int b2_registry_load(b2_ctx* ctx, const uint8_t* pk48, const uint64_t* eff, cons
     CKL(ctx);
     if (pk_valid_out) CK(cudaMemcpyAsync(pk_valid_out, ctx->d_valid, n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    for (int w = 0; w < 2; w++)
+        if (ctx->d_part[w]) {
+            cudaFree(ctx->d_part[w]);
+            ctx->d_part[w] = nullptr;
+        }
+    if (ctx->d_part_first) {
+        cudaFree(ctx->d_part_first);
+        ctx->d_part_first = nullptr;
+    }
     ctx->n_val = n;
     return B2_OK;
 }
@@ -736,6 +748,57 @@ int b2_latest_messages_update(b2_ctx* ctx, const uint32_t* members, const uint32
                                             (const uint64_t*)ctx->in_d.p, (const uint32_t*)ctx->in_e.p, accept ? (const uint8_t*)ctx->in_f.p : nullptr,
                                             n_agg, s)))
         return rc;
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------ participation flags (process_attestation :738-754)
+int b2_participation_load(b2_ctx* ctx, int which, const uint8_t* participation, uint64_t n) {
+    REQUIRE(ctx && (which == 0 || which == 1) && participation && n == ctx->n_val && n > 0, "participation_load: bad arguments / registry size");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    const size_t words = (n + 3) / 4;
+    if (!ctx->d_part[which] && (rc = dev_alloc(ctx, &ctx->d_part[which], words))) return rc;
+    if (!ctx->d_part_first) {
+        if ((rc = dev_alloc(ctx, &ctx->d_part_first, 3 * n))) return rc;
+        CK(cudaMemsetAsync(ctx->d_part_first, 0xff, 3 * n * 4, ctx->s_main));
+    }
+    CK(cudaMemsetAsync(ctx->d_part[which], 0, words * 4, ctx->s_main));
+    CK(cudaMemcpyAsync(ctx->d_part[which], participation, n, cudaMemcpyHostToDevice, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    return B2_OK;
+}
+int b2_participation_read(b2_ctx* ctx, int which, uint8_t* participation_out, uint64_t n) {
+    REQUIRE(ctx && (which == 0 || which == 1) && participation_out && n == ctx->n_val && ctx->d_part[which], "participation_read: not loaded / bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(participation_out, ctx->d_part[which], n, cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    return B2_OK;
+}
+int b2_participation_update(b2_ctx* ctx, int which, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
+                            const uint8_t* flag_mask, const uint8_t* accept, uint32_t n_agg, uint64_t effective_balance_increment,
+                            uint64_t base_reward_per_increment, uint64_t* numerator_out) {
+    REQUIRE(ctx && (which == 0 || which == 1) && members && off && bits && flag_mask && numerator_out && n_agg > 0 && bits_stride > 0 &&
+                effective_balance_increment > 0, "participation_update: bad arguments");
+    REQUIRE(ctx->n_val > 0 && ctx->d_part[which], "participation_update: registry / participation table not loaded");
+    int rc;
+    if ((rc = check_batch(ctx, members, off, bits_stride, n_agg, ctx->n_val))) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    if ((rc = upload_batch(ctx, members, off, bits, bits_stride, n_agg, s))) return rc;
+    if ((rc = ensure(ctx, ctx->in_d, n_agg)) || (rc = ensure(ctx, ctx->in_f, n_agg)) || (rc = ensure(ctx, ctx->out_a, (size_t)n_agg * 8))) return rc;
+    CK(cudaMemcpyAsync(ctx->in_d.p, flag_mask, n_agg, cudaMemcpyHostToDevice, s));
+    if (accept) CK(cudaMemcpyAsync(ctx->in_f.p, accept, n_agg, cudaMemcpyHostToDevice, s));
+    const uint32_t *dm = (const uint32_t*)ctx->in_a.p, *dof = (const uint32_t*)ctx->in_b.p;
+    const uint8_t *db = (const uint8_t*)ctx->in_c.p, *dmask = (const uint8_t*)ctx->in_d.p, *dacc = accept ? (const uint8_t*)ctx->in_f.p : nullptr;
+    k_part_phase1<<<n_agg, 128, 0, s>>>(dm, dof, db, bits_stride, dmask, dacc, n_agg, (const uint8_t*)ctx->d_part[which], ctx->d_part_first);
+    CKL(ctx);
+    k_part_phase2<<<n_agg, 128, 0, s>>>(dm, dof, db, bits_stride, dmask, dacc, n_agg, ctx->d_part_first, ctx->d_eff, effective_balance_increment,
+                                        base_reward_per_increment, (unsigned long long*)ctx->out_a.p);
+    CKL(ctx);
+    k_part_phase3<<<n_agg, 128, 0, s>>>(dm, dof, db, bits_stride, dmask, dacc, n_agg, ctx->d_part_first, ctx->d_part[which]);
+    CKL(ctx);
+    CK(cudaMemcpyAsync(numerator_out, ctx->out_a.p, (size_t)n_agg * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return B2_OK;
 }

@@ -713,3 +713,81 @@ __global__ void __launch_bounds__(64) k_signing_roots(const uint8_t* __restrict_
     for (int k = 0; k < 32; k++) out32[32 * (uint64_t)i + k] = o[k];
 }
 }  // namespace b2
+
+// ------------------------------------------------------------------------------------------ participation flags + proposer-reward numerators
+// The bookkeeping loop of process_attestation (/root/reference/pos-evolution.md:745-749): for every attesting index and every
+// flag the attestation earns, set the flag if it is not set yet and credit get_base_reward(index) * weight to THIS
+// attestation's proposer_reward_numerator.  Which attestation of a batch gets the credit matters (the numerator is divided
+// per attestation, :752-754), so the parallel form is order-exact like K7: phase 1 elects, per (validator, flag), the
+// earliest accepted attestation of the list that earns the still-unset flag (atomicMin on its list position); phase 2 sums
+// the rewards of the elections each attestation won; phase 3 sets the flags and re-arms the election table.
+namespace b2 {
+__device__ __forceinline__ bool part_member(const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t stride, uint32_t a, uint32_t j,
+                                            uint32_t& v) {
+    if (!((bits[(uint64_t)a * stride + (j >> 3)] >> (j & 7)) & 1)) return false;
+    v = members[off[a] + j];
+    return true;
+}
+__global__ void __launch_bounds__(128) k_part_phase1(const uint32_t* __restrict__ members, const uint32_t* __restrict__ off,
+                                                      const uint8_t* __restrict__ bits, uint32_t stride, const uint8_t* __restrict__ flag_mask,
+                                                      const uint8_t* __restrict__ accept, uint32_t n_agg, const uint8_t* __restrict__ part,
+                                                      uint32_t* first) {
+    const uint32_t a = blockIdx.x;
+    if (a >= n_agg || (accept && !accept[a])) return;
+    const uint32_t mask = flag_mask[a] & 7u, size = off[a + 1] - off[a];
+    uint32_t v;
+    for (uint32_t j = threadIdx.x; j < size; j += blockDim.x)
+        if (part_member(members, off, bits, stride, a, j, v)) {
+            const uint32_t need = mask & ~(uint32_t)part[v];
+#pragma unroll
+            for (int f = 0; f < 3; f++)
+                if ((need >> f) & 1u) atomicMin(&first[3 * (uint64_t)v + f], a);
+        }
+}
+// weights = PARTICIPATION_FLAG_WEIGHTS (14, 26, 14); reward unit = (effective_balance / increment) * base_reward_per_increment
+__global__ void __launch_bounds__(128) k_part_phase2(const uint32_t* __restrict__ members, const uint32_t* __restrict__ off,
+                                                      const uint8_t* __restrict__ bits, uint32_t stride, const uint8_t* __restrict__ flag_mask,
+                                                      const uint8_t* __restrict__ accept, uint32_t n_agg, const uint32_t* __restrict__ first,
+                                                      const uint64_t* __restrict__ eff, unsigned long long increment, unsigned long long per_increment,
+                                                      unsigned long long* numerator) {
+    __shared__ unsigned long long red[4];
+    const uint32_t a = blockIdx.x;
+    if (a >= n_agg) return;
+    unsigned long long sum = 0;
+    if (!accept || accept[a]) {
+        const uint32_t mask = flag_mask[a] & 7u, size = off[a + 1] - off[a];
+        uint32_t v;
+        for (uint32_t j = threadIdx.x; j < size; j += blockDim.x)
+            if (part_member(members, off, bits, stride, a, j, v)) {
+                const unsigned long long base = (eff[v] / increment) * per_increment;
+                if ((mask & 1u) && first[3 * (uint64_t)v + 0] == a) sum += base * 14ull;
+                if ((mask & 2u) && first[3 * (uint64_t)v + 1] == a) sum += base * 26ull;
+                if ((mask & 4u) && first[3 * (uint64_t)v + 2] == a) sum += base * 14ull;
+            }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_down_sync(B2_FULL_MASK, sum, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) numerator[a] = red[0] + red[1] + red[2] + red[3];
+}
+__global__ void __launch_bounds__(128) k_part_phase3(const uint32_t* __restrict__ members, const uint32_t* __restrict__ off,
+                                                      const uint8_t* __restrict__ bits, uint32_t stride, const uint8_t* __restrict__ flag_mask,
+                                                      const uint8_t* __restrict__ accept, uint32_t n_agg, uint32_t* first, uint32_t* part_words) {
+    const uint32_t a = blockIdx.x;
+    if (a >= n_agg || (accept && !accept[a])) return;
+    const uint32_t mask = flag_mask[a] & 7u, size = off[a + 1] - off[a];
+    uint32_t v;
+    for (uint32_t j = threadIdx.x; j < size; j += blockDim.x)
+        if (part_member(members, off, bits, stride, a, j, v)) {
+            uint32_t won = 0;
+#pragma unroll
+            for (int f = 0; f < 3; f++)
+                if (((mask >> f) & 1u) && first[3 * (uint64_t)v + f] == a) {
+                    won |= 1u << f;
+                    first[3 * (uint64_t)v + f] = 0xffffffffu;       // single writer: only the elected attestation resets
+                }
+            if (won) atomicOr(&part_words[v >> 2], won << (8 * (v & 3)));
+        }
+}
+}  // namespace b2

@@ -198,6 +198,25 @@ class Engine:
         acc = _c(accept, np.uint8) if accept is not None else None
         self._ck(self.lib.b2_latest_messages_update(self.h, _p(members), _p(off), _p(bits), stride, _p(te), _p(bi), _p(acc), n_agg))
 
+    def participation_load(self, which: int, participation):
+        p = _c(participation, np.uint8)
+        self._ck(self.lib.b2_participation_load(self.h, int(which), _p(p), p.shape[0]))
+
+    def participation_read(self, which: int):
+        out = np.zeros(self.n_validators, dtype=np.uint8)
+        self._ck(self.lib.b2_participation_read(self.h, int(which), _p(out), self.n_validators))
+        return out
+
+    def participation_update(self, which, members, off, bits, flag_mask, accept, increment, base_reward_per_increment):
+        """process_attestation's flag loop (:745-749) for a batch; returns the per-attestation proposer_reward_numerator (u64)."""
+        members, off, bits, n_agg, stride = self._batch(members, off, bits)
+        fm = _c(flag_mask, np.uint8)
+        acc = _c(accept, np.uint8) if accept is not None else None
+        num = np.zeros(n_agg, dtype=np.uint64)
+        self._ck(self.lib.b2_participation_update(self.h, int(which), _p(members), _p(off), _p(bits), stride, _p(fm), _p(acc), n_agg,
+                                                  int(increment), int(base_reward_per_increment), _p(num)))
+        return num
+
     def tree_load(self, parent, slot, roots32, leaf_viable):
         parent, slot = _c(parent, np.uint32), _c(slot, np.uint64)
         roots = _c(roots32, np.uint8).reshape(-1, 32)

@@ -467,9 +467,41 @@ class Spec:
                 pre.append(None)
                 break
         verdicts = self.are_valid_indexed_attestations(state, [p[2] for p in pre if p is not None])
-        for k, att in enumerate(attestations):
-            assert k < len(pre) and pre[k] is not None and verdicts[k]
-            self._apply_attestation(state, att, pre[k][0], pre[k][1])
+        n_ok = 0
+        while n_ok < len(attestations) and n_ok < len(pre) and pre[n_ok] is not None and verdicts[n_ok]:
+            n_ok += 1
+        if n_ok and hasattr(self.engine, "participation_update"):
+            self._apply_attestations_gpu(state, attestations[:n_ok], pre[:n_ok])
+        else:
+            for k in range(n_ok):
+                self._apply_attestation(state, attestations[k], pre[k][0], pre[k][1])
+        assert n_ok == len(attestations)
+
+    def _apply_attestations_gpu(self, state, attestations, pre):
+        """Flag scatter + proposer-reward numerators of :745-752 for a prefix of valid attestations on the GPU (order-exact),
+        then the per-attestation integer division and the proposer credit of :752-754 on the host."""
+        eng = self.engine
+        cur = self.get_current_epoch(state)
+        tables = (state.current_epoch_participation, state.previous_epoch_participation)
+        per_inc = self.get_base_reward_per_increment(state)
+        denominator = (WEIGHT_DENOMINATOR - PROPOSER_WEIGHT) * WEIGHT_DENOMINATOR // PROPOSER_WEIGHT
+        proposer = self.get_beacon_proposer_index(state)
+        for which in (0, 1):
+            sel = [k for k, att in enumerate(attestations) if (att.data.target.epoch == cur) == (which == 0)]
+            if not sel:
+                continue
+            members, off, rows, masks = [], [0], [], []
+            for k in sel:
+                members += pre[k][0]
+                off.append(len(members))
+                rows.append(attestations[k].aggregation_bits)
+                masks.append(sum(1 << f for f in pre[k][1]))
+            eng.participation_load(which, np.asarray(tables[which], dtype=np.uint8))
+            num = eng.participation_update(which, np.asarray(members, dtype=np.uint32), off, pack_bits(rows), np.asarray(masks, dtype=np.uint8), None,
+                                           self.p.EFFECTIVE_BALANCE_INCREMENT, per_inc)
+            tables[which][:] = eng.participation_read(which).tolist()
+            for v in num:
+                state.balances[proposer] += int(v) // denominator
 
     # ------------------------------------------------------------------ fork choice
     def update_latest_messages(self, store, attesting_indices, attestation):   # :1435-1441 (host dict form)
