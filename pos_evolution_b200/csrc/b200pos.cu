@@ -294,7 +294,7 @@ static int aggregate_front(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, const 
         k_g2_decompress<<<blocks_for(n_sig, 128), 128, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p);
         CKL(ctx);
     }
-    k_g2_segment_sum<<<n_seg, 128, 0, s>>>((const uint32_t*)ctx->sc_g2aff.p, (const uint8_t*)ctx->sc_g2st.p, d_seg_off, n_seg,
+    k_g2_segment_sum<<<n_seg, 32, 0, s>>>((const uint32_t*)ctx->sc_g2aff.p, (const uint8_t*)ctx->sc_g2st.p, d_seg_off, n_seg,
                                            (uint32_t*)V.sumjac.p, d_seg_status);
     CKL(ctx);
     return B2_OK;
@@ -849,7 +849,7 @@ int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, cons
         rank_p[p] = rank[b];
     }
     if ((rc = dev_alloc(ctx, &ctx->d_pre, n)) || (rc = dev_alloc(ctx, &ctx->d_inv, n)) || (rc = dev_alloc(ctx, &ctx->d_size_keep, n)) ||
-        (rc = dev_alloc(ctx, &ctx->d_rank, n)) || (rc = dev_alloc(ctx, &ctx->d_next, n)) || (rc = dev_alloc(ctx, &ctx->d_gsize, n)) ||
+        (rc = dev_alloc(ctx, &ctx->d_rank, n)) || (rc = dev_alloc(ctx, &ctx->d_next, (size_t)n + 1)) || (rc = dev_alloc(ctx, &ctx->d_gsize, n)) ||
         (rc = dev_alloc(ctx, &ctx->d_votes, n)) || (rc = dev_alloc(ctx, &ctx->d_prefix, (size_t)n + 1)) || (rc = dev_alloc(ctx, &ctx->d_w2, n)) ||
         (rc = dev_alloc(ctx, &ctx->d_weight, n)) || (rc = dev_alloc(ctx, &ctx->d_head, 1)))
         return rc;
@@ -905,7 +905,7 @@ int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t jus
     A.justified = justified_idx;
     A.boost_idx = boost_idx;
     A.boost_score = boost_score;
-    size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8;
+    size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8 + 8;
     A.use_smem = smem <= 226 * 1024 && A.n <= 15 * 1024;   // 227 KB per block minus the kernel's static shared memory
     k_ghost_tree<<<1, 1024, A.use_smem ? smem : 0, s>>>(A);
     CKL(ctx);

@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(128, 4) k_g2_decompress(const uint8_t* __restr
     for (int k = 0; k < 12; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
     st_out[i] = (uint8_t)st;
 }
-// stage 2: one block per segment: mixed additions + tree -> Jacobian sum (72 words) + status.  The inversion needed for
+// stage 2: one WARP per segment (each lane adds every 32nd point, then a 5-round shuffle tree) -> Jacobian sum (72 words) + status.  The inversion needed for
 // the compressed encoding is NOT done here (127 threads would idle behind it): stage 3 does it with a thread per segment.
-__global__ void __launch_bounds__(128, 3) k_g2_segment_sum(const uint32_t* __restrict__ aff, const uint8_t* __restrict__ st,
+__global__ void __launch_bounds__(32) k_g2_segment_sum(const uint32_t* __restrict__ aff, const uint8_t* __restrict__ st,
                                                             const uint32_t* __restrict__ seg_off, uint32_t n_seg, uint32_t* sum_jac,
                                                             int32_t* seg_status) {
     __shared__ g2_jac red[4];
@@ -447,14 +447,20 @@ __global__ void __launch_bounds__(1024) k_ghost_votes_smem(uint64_t n, const uns
                 }
             }
         }
-        unsigned peers = __match_any_sync(B2_FULL_MASK, b);
-        unsigned long long sum = 0;
+        // fast path: the whole warp votes for one block (the common case on a healthy chain): one shuffle reduction, one
+        // shared-memory atomic.  Otherwise every lane adds into the CTA-private bins itself (shared-memory atomics).
+        const unsigned voting = __ballot_sync(B2_FULL_MASK, on);
+        if (voting == 0) continue;
+        const uint32_t b0 = __shfl_sync(B2_FULL_MASK, b, __ffs(voting) - 1);
+        const bool uniform = __all_sync(B2_FULL_MASK, !on || b == b0);
+        if (uniform) {
+            unsigned long long sum = bal;
 #pragma unroll
-        for (int l = 0; l < 32; l++) {
-            unsigned long long o = __shfl_sync(B2_FULL_MASK, bal, l);
-            if ((peers >> l) & 1u) sum += o;
+            for (int d = 16; d >= 1; d >>= 1) sum += __shfl_down_sync(B2_FULL_MASK, sum, d);
+            if (lane == 0) atomicAdd(&bins[b0], sum);
+        } else if (on) {
+            atomicAdd(&bins[b], bal);
         }
-        if (on && lane == __ffs(peers) - 1) atomicAdd(&bins[b], sum);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_blocks; i += blockDim.x) {
@@ -468,10 +474,12 @@ __global__ void __launch_bounds__(1024) k_ghost_votes_smem(uint64_t n, const uns
 //   * the subtree of the block at position p is the contiguous range [p, p + size[p]) and its
 //     get_latest_attesting_balance is a difference of two prefix sums of the direct votes (+ boost on one block);
 //   * the children of p are p+1, p+1+size[p+1], ... -- no child lists;
-//   * all loads are coalesced and everything the head walk touches lives in shared memory (16 B per block).
-// The head walk of get_head (argmax over children of (weight, root), repeated down to a leaf) is done for all blocks at
-// once: best_child[], then pointer jumping (ceil(log2 n) rounds) from the justified root.  Trees too large for shared
-// memory (> ~14 000 blocks) use the same code on global scratch.
+//   * all loads are coalesced and everything lives in shared memory (16 B per block).
+// The head walk of get_head (argmax over children of (weight, root), repeated down to a leaf) needs no pointer chasing:
+// mark every block that is NOT the best child of its parent; a block lies on the head path iff no block on its root path is
+// marked, i.e. iff the number of marked ancestors-or-self is zero.  That count is a second prefix sum (+1 at the marked block,
+// -1 past its subtree), and the head is the last pre-order position with count zero -- two scans and a max-reduction
+// instead of log2(n) rounds over all blocks.  Trees too large for shared memory use the same code on global scratch.
 struct ghost_tree_args {
     uint32_t n;
     const uint32_t* pre;         // block -> pre-order position
@@ -482,7 +490,7 @@ struct ghost_tree_args {
     unsigned long long* g_w;     // global fallback scratch n+1 (prefix sums)
     unsigned long long* g_w2;    // global fallback scratch n (weights)
     uint32_t* g_size;            // global fallback scratch n
-    uint32_t* g_next;            // global fallback scratch n
+    uint32_t* g_next;            // global fallback scratch n+1 (marks / counts)
     unsigned long long* weight_out;  // optional, per block (original numbering)
     uint32_t* head_out;
     uint32_t justified;
@@ -490,14 +498,55 @@ struct ghost_tree_args {
     unsigned long long boost_score;
     int use_smem;
 };
+
+// exclusive prefix sum of x[0..n) in place, x[n] = total; every thread of the block must call it
+template <class T> __device__ __forceinline__ void block_exclusive_scan(T* x, uint32_t n, T* warp_tot) {
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    const uint32_t per = (n + nthr - 1) / nthr;
+    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
+    T local = 0;
+    for (uint32_t i = lo; i < hi; i++) local += x[i];
+    T incl = local;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(B2_FULL_MASK, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        T w = (lane < (int)(nthr >> 5)) ? warp_tot[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            T o = __shfl_up_sync(B2_FULL_MASK, wi, d);
+            if (lane >= d) wi += o;
+        }
+        warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    T run = warp_tot[warp] + incl - local;
+    for (uint32_t i = lo; i < hi; i++) {
+        T v = x[i];
+        x[i] = run;
+        run += v;
+    }
+    if (lo < n && hi == n) x[n] = run;
+    if (n == 0 && tid == 0) x[0] = 0;
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
     extern __shared__ unsigned long long smem_u64[];
     __shared__ unsigned long long warp_tot[32];
+    __shared__ uint32_t warp_tot32[32];
+    __shared__ uint32_t head_pos;
     const uint32_t n = A.n, tid = threadIdx.x, T = blockDim.x;
     unsigned long long* W = A.use_smem ? smem_u64 : A.g_w;                                     // n+1: votes -> prefix -> weights
     uint32_t* size = A.use_smem ? reinterpret_cast<uint32_t*>(smem_u64 + (n + 1)) : A.g_size;   // n
-    uint32_t* next = A.use_smem ? size + n : A.g_next;                                          // n
+    uint32_t* mark = A.use_smem ? size + n : A.g_next;                                          // n+1: marks -> counts
     const uint32_t boost_p = A.boost_idx >= 0 ? A.pre[A.boost_idx] : 0xffffffffu;
+    if (tid == 0) head_pos = 0;
     // stage votes (+ boost) and sizes, coalesced; leave the global accumulator clean for the next call
     for (uint32_t p = tid; p < n; p += T) {
         unsigned long long v = A.votes[p];
@@ -505,41 +554,11 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
         if (p == boost_p) v += A.boost_score;
         W[p] = v;
         size[p] = A.size_keep[p];
+        mark[p] = 0;
     }
+    if (tid == 0) mark[n] = 0;
     __syncthreads();
-    // exclusive prefix sum over W[0..n): thread t owns the contiguous chunk [lo, hi)
-    const uint32_t per = (n + T - 1) / T;
-    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
-    unsigned long long local = 0;
-    for (uint32_t i = lo; i < hi; i++) local += W[i];
-    unsigned long long incl = local;
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long o = __shfl_up_sync(B2_FULL_MASK, incl, d);
-        if (lane >= d) incl += o;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long w = (lane < (int)(T >> 5)) ? warp_tot[lane] : 0, wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned long long o = __shfl_up_sync(B2_FULL_MASK, wi, d);
-            if (lane >= d) wi += o;
-        }
-        warp_tot[lane] = wi - w;
-    }
-    __syncthreads();
-    unsigned long long run = warp_tot[warp] + incl - local;
-    for (uint32_t i = lo; i < hi; i++) {
-        unsigned long long v = W[i];
-        W[i] = run;
-        run += v;
-    }
-    if (lo < n && hi == n) W[n] = run;
-    if (n == 0 && tid == 0) W[0] = 0;
-    __syncthreads();
+    block_exclusive_scan(W, n, warp_tot);
     // weights: w[p] = S[p + size] - S[p].  Shared-memory mode overwrites S in place (through registers: the smem budget
     // caps n at ~14 500 = 15 per thread); global mode writes a separate array.
     unsigned long long* Wt = A.use_smem ? W : A.g_w2;
@@ -563,38 +582,48 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
     __syncthreads();
     if (A.weight_out)
         for (uint32_t b = tid; b < n; b += T) A.weight_out[b] = Wt[A.pre[b]];
-    // best child of every kept block
+    // every child that is not its parent's best child gets +1 at its position and -1 just past its subtree
+    const uint32_t jp = A.justified < n ? A.pre[A.justified] : 0;
     for (uint32_t p = tid; p < n; p += T) {
         const uint32_t sk = size[p];
-        uint32_t best = p;
+        const uint32_t end = p + (sk & 0x7fffffffu);
+        if (p + 1 >= end) continue;
+        uint32_t best = 0xffffffffu;
         if (sk >> 31) {
-            const uint32_t end = p + (sk & 0x7fffffffu);
             unsigned long long bw = 0;
-            bool have = false;
             for (uint32_t c = p + 1; c < end; c += size[c] & 0x7fffffffu) {
                 if (!(size[c] >> 31)) continue;
                 const unsigned long long w = Wt[c];
-                if (!have || w > bw || (w == bw && A.rank[c] > A.rank[best])) {
-                    have = true;
+                if (best == 0xffffffffu || w > bw || (w == bw && A.rank[c] > A.rank[best])) {
                     best = c;
                     bw = w;
                 }
             }
         }
-        next[p] = best;
+        for (uint32_t c = p + 1; c < end; c += size[c] & 0x7fffffffu)
+            if (c != best) {
+                atomicAdd(&mark[c], 1u);
+                atomicAdd(&mark[c + (size[c] & 0x7fffffffu)], 0xffffffffu);     // -1 (mod 2^32); position n is the sentinel slot
+            }
     }
     __syncthreads();
-    // pointer jumping, in place: a racing reader sees the old or the new hop target of another block; both lie on the same
-    // best path, the hop distance at least doubles per round, and the fix point is the leaf
-    volatile uint32_t* vn = next;
-    for (uint32_t span = 1; span < n; span <<= 1) {
-        for (uint32_t p = tid; p < n; p += T) {
-            uint32_t t2 = vn[vn[p]];
-            vn[p] = t2;
+    block_exclusive_scan(mark, n, warp_tot32);          // mark[p] = number of marked proper ancestors ... of positions < p
+    // after the scan mark[p+1] is the inclusive count at p = number of marked blocks among p and its ancestors.  The head path
+    // below the justified block = the positions of its subtree whose count equals the justified block's own count
+    // (nothing marked in between); the head is the last of them in pre-order.
+    const uint32_t base = mark[jp + 1];
+    const uint32_t jend = jp + (size[jp] & 0x7fffffffu);
+    uint32_t best_pos = 0;
+    bool have = false;
+    for (uint32_t p = jp + tid; p < jend; p += T) {
+        if (mark[p + 1] == base) {
+            best_pos = p;
+            have = true;
         }
-        __syncthreads();
     }
-    if (tid == 0) *A.head_out = (A.justified < n) ? A.inv[next[A.pre[A.justified]]] : 0xffffffffu;
+    if (have) atomicMax(&head_pos, best_pos);
+    __syncthreads();
+    if (tid == 0) *A.head_out = (A.justified < n) ? A.inv[max(head_pos, jp)] : 0xffffffffu;
 }
 
 }  // namespace b2
