@@ -126,6 +126,14 @@ int b2_participation_update(b2_ctx* ctx, int which, const uint32_t* members, con
                             const uint8_t* flag_mask, const uint8_t* accept, uint32_t n_agg, uint64_t effective_balance_increment,
                             uint64_t base_reward_per_increment, uint64_t* numerator_out);
 
+/* ---- fork-choice variants (pos-evolution.md:1411-1413, :1447-1461, :1549-1596):
+ * b2_set_fork_choice_params: votes whose epoch is < min_vote_epoch do not count (vote expiry of the Goldfish / RLMD-GHOST family;
+ *   0 = plain LMD-GHOST); exclude_slashed != 0 selects the v1.3 get_weight rule (slashed validators, registry flag bit1, do not count).
+ * b2_on_attester_slashing: the validators present in BOTH sorted index lists become equivocating (Store.equivocating_indices)
+ *   and stop counting; validity of the slashing itself (:1453-1457) is the caller's job. */
+int b2_set_fork_choice_params(b2_ctx* ctx, uint64_t min_vote_epoch, int exclude_slashed);
+int b2_on_attester_slashing(b2_ctx* ctx, const uint32_t* indices_1, uint32_t n1, const uint32_t* indices_2, uint32_t n2);
+
 /* Store.blocks (pos-evolution.md:898) as arrays in topological order (parent[b] < b, parent[0] ignored; block 0 =
  * store.justified_checkpoint.root).  leaf_viable[b]: the get_filtered_block_tree leaf test (:1104, prose :1121-1124). */
 int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, const uint8_t* root32, const uint8_t* leaf_viable,

@@ -40,6 +40,9 @@ struct b2_ctx {
     unsigned long long* d_lmd_key = nullptr;
     uint32_t* d_lmd_block = nullptr;
     uint8_t* d_equiv = nullptr;
+    // fork-choice variants: votes older than fc_min_key (epoch << 32) expire; v1.3 get_weight skips slashed validators
+    unsigned long long fc_min_key = 0;
+    int fc_exclude_slashed = 0;
     // epoch participation flags (0 = current, 1 = previous) and the per-(validator, flag) election table
     uint32_t* d_part[2] = {nullptr, nullptr};
     uint32_t* d_part_first = nullptr;
@@ -359,7 +362,33 @@ struct pk_source {
     const uint8_t* d_pk48;      // explicit-key form when non-null (d_off = pk offsets)
     uint64_t n_pk;
 };
-static int verify_fork(b2_ctx* ctx, vslot& V, const pk_source& P, const uint8_t* d_msg32, uint32_t n_agg, cudaStream_t s) {
+// Two forms of K5/K6.  `team`: three lanes per pairing -- shortest critical path, used when the caller waits for the result
+// (synchronous entry points).  Thread-per-item: 2.7x longer, but ~40 % fewer warp instructions in total -- used by the pipelined
+// epoch API, where the latency hides behind the next epoch's decompression and only the stolen multiply-pipe time counts.
+static int launch_miller(b2_ctx* ctx, vslot& V, uint32_t n_agg, int mode, bool team, cudaStream_t s) {
+    if (team) {
+        k_miller_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, s>>>(
+            (const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p, (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p,
+            (const uint8_t*)V.sflag.p, n_agg, (uint32_t*)V.f.p, mode);
+    } else {
+        k_miller<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p,
+                                                      (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p, (const uint8_t*)V.sflag.p, n_agg,
+                                                      (uint32_t*)V.f.p, mode);
+    }
+    CKL(ctx);
+    return B2_OK;
+}
+static int launch_final(b2_ctx* ctx, vslot& V, uint32_t n_agg, uint8_t* d_ok, bool team, cudaStream_t s) {
+    if (team) {
+        k_final_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, s>>>((const uint32_t*)V.f.p, (const uint8_t*)V.pkst.p,
+                                                                                  (const uint8_t*)V.sflag.p, n_agg, d_ok);
+    } else {
+        k_final_verdict<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)V.f.p, (const uint8_t*)V.pkst.p, (const uint8_t*)V.sflag.p, n_agg, d_ok);
+    }
+    CKL(ctx);
+    return B2_OK;
+}
+static int verify_fork(b2_ctx* ctx, vslot& V, const pk_source& P, const uint8_t* d_msg32, uint32_t n_agg, cudaStream_t s, bool team = true) {
     int rc;
     if ((rc = ensure(ctx, V.haff, (size_t)n_agg * 192)) || (rc = ensure(ctx, V.hflag, n_agg)) || (rc = ensure(ctx, V.saff, (size_t)n_agg * 192)) ||
         (rc = ensure(ctx, V.sflag, n_agg)) || (rc = ensure(ctx, V.f, (size_t)n_agg * 2 * 576)) || (rc = ensure(ctx, V.pkjac, (size_t)n_agg * 144)) ||
@@ -386,28 +415,20 @@ static int verify_fork(b2_ctx* ctx, vslot& V, const pk_source& P, const uint8_t*
         CKL(ctx);
     }
     CK(cudaStreamWaitEvent(ctx->s_aux[1], V.ev_join0, 0));
-    k_miller_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, ctx->s_aux[1]>>>(
-        (const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p, (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p,
-        (const uint8_t*)V.sflag.p, n_agg, (uint32_t*)V.f.p, 1);
-    CKL(ctx);
+    if ((rc = launch_miller(ctx, V, n_agg, 1, team, ctx->s_aux[1]))) return rc;
     CK(cudaEventRecord(V.ev_join1, ctx->s_aux[1]));
     return B2_OK;
 }
 // d_sig96 == nullptr: the signature points are already in V.saff / V.sflag (handed over by aggregate_finish)
-static int verify_main(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s) {
+static int verify_main(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s, bool team = true) {
+    int rc;
     if (d_sig96) {
         k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, s>>>(d_sig96, n_agg, (uint32_t*)V.saff.p, (uint8_t*)V.sflag.p);
         CKL(ctx);
     }
-    k_miller_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, s>>>(
-        (const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p, (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p,
-        (const uint8_t*)V.sflag.p, n_agg, (uint32_t*)V.f.p, 2);
-    CKL(ctx);
+    if ((rc = launch_miller(ctx, V, n_agg, 2, team, s))) return rc;
     CK(cudaStreamWaitEvent(s, V.ev_join1, 0));
-    k_final_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, s>>>((const uint32_t*)V.f.p, (const uint8_t*)V.pkst.p,
-                                                                              (const uint8_t*)V.sflag.p, n_agg, d_ok);
-    CKL(ctx);
-    return B2_OK;
+    return launch_final(ctx, V, n_agg, d_ok, team, s);
 }
 
 int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
@@ -430,24 +451,24 @@ int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const u
 //                bound work on few SMs; on `tail_stream` (the caller's own stream, or the context's tail stream so that
 //                it overlaps with the next epoch's epoch_start in the other slot).
 static int epoch_start(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
-                       uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, cudaStream_t s) {
+                       uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, cudaStream_t s, bool team) {
     vslot& V = ctx->slot[slot];
     int rc;
     CK(cudaStreamWaitEvent(s, V.ev_tail_done, 0));      // the slot's previous user (two epochs ago) must have drained
     pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
-    if ((rc = verify_fork(ctx, V, P, d_msg32, n_agg, s))) return rc;
+    if ((rc = verify_fork(ctx, V, P, d_msg32, n_agg, s, team))) return rc;
     if ((rc = aggregate_front(ctx, V, d_sig96, d_off, n_agg, n_sig, d_agg_status, s))) return rc;
     CK(cudaEventRecord(V.ev_seg, s));
     return B2_OK;
 }
 static int epoch_tail(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
                       const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
-                      uint8_t* d_ok_out, cudaStream_t t) {
+                      uint8_t* d_ok_out, cudaStream_t t, bool team) {
     vslot& V = ctx->slot[slot];
     int rc;
     CK(cudaStreamWaitEvent(t, V.ev_seg, 0));
     if ((rc = aggregate_finish(ctx, V, n_agg, d_agg_sig96, d_agg_status, true, t))) return rc;
-    if ((rc = verify_main(ctx, V, nullptr, n_agg, d_ok_out, t))) return rc;
+    if ((rc = verify_main(ctx, V, nullptr, n_agg, d_ok_out, t, team))) return rc;
     CK(cudaStreamWaitEvent(t, ctx->ev_votes_done, 0));  // do not move the LMD table under a vote scatter that is still reading it
     if ((rc = b2_latest_messages_update_dev(ctx, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_ok_out, n_agg, t))) return rc;
     CK(cudaEventRecord(V.ev_tail_done, t));
@@ -463,8 +484,8 @@ int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members,
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if ((rc = epoch_start(ctx, 0, d_sig96, d_members, d_off, d_bits, bits_stride, d_msg32, n_agg, n_sig, d_agg_status, s))) return rc;
-    return epoch_tail(ctx, 0, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, n_agg, d_agg_sig96, d_agg_status, d_ok_out, s);
+    if ((rc = epoch_start(ctx, 0, d_sig96, d_members, d_off, d_bits, bits_stride, d_msg32, n_agg, n_sig, d_agg_status, s, true))) return rc;
+    return epoch_tail(ctx, 0, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, n_agg, d_agg_sig96, d_agg_status, d_ok_out, s, true);
 }
 
 // Pipelined form: call start(slot), then [finish the previous epoch: b2_epoch_wait_dev(other slot) + vote weights + head], then
@@ -475,7 +496,7 @@ int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint
             "epoch_start_dev: bad arguments");
     REQUIRE(ctx->n_val > 0, "epoch_start_dev: registry not loaded");
     CK(cudaSetDevice(ctx->device));
-    return epoch_start(ctx, slot, d_sig96, d_members, d_off, d_bits, bits_stride, d_msg32, n_agg, n_sig, d_agg_status, (cudaStream_t)stream);
+    return epoch_start(ctx, slot, d_sig96, d_members, d_off, d_bits, bits_stride, d_msg32, n_agg, n_sig, d_agg_status, (cudaStream_t)stream, false);
 }
 int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
                       const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
@@ -484,7 +505,7 @@ int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const ui
                 n_agg > 0 && bits_stride > 0, "epoch_tail_dev: bad arguments");
     CK(cudaSetDevice(ctx->device));
     return epoch_tail(ctx, slot, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, n_agg, d_agg_sig96, d_agg_status, d_ok_out,
-                      ctx->s_tail);
+                      ctx->s_tail, false);
 }
 int b2_epoch_wait_dev(b2_ctx* ctx, int slot, void* stream) {
     REQUIRE(ctx && (slot == 0 || slot == 1), "epoch_wait_dev: bad arguments");
@@ -803,6 +824,31 @@ int b2_participation_update(b2_ctx* ctx, int which, const uint32_t* members, con
     return B2_OK;
 }
 
+// ------------------------------------------------------------------------------------------ fork-choice variants
+int b2_set_fork_choice_params(b2_ctx* ctx, uint64_t min_vote_epoch, int exclude_slashed) {
+    REQUIRE(ctx && min_vote_epoch < 0xffffffffull, "set_fork_choice_params: bad arguments");
+    ctx->fc_min_key = (unsigned long long)min_vote_epoch << 32;
+    ctx->fc_exclude_slashed = exclude_slashed ? 1 : 0;
+    return B2_OK;
+}
+
+int b2_on_attester_slashing(b2_ctx* ctx, const uint32_t* indices_1, uint32_t n1, const uint32_t* indices_2, uint32_t n2) {
+    REQUIRE(ctx && ctx->n_val > 0 && (n1 == 0 || indices_1) && (n2 == 0 || indices_2), "on_attester_slashing: bad arguments / registry not loaded");
+    for (uint32_t i = 1; i < n1; i++) REQUIRE(indices_1[i - 1] < indices_1[i], "on_attester_slashing: attesting_indices must be sorted and unique");
+    for (uint32_t i = 1; i < n2; i++) REQUIRE(indices_2[i - 1] < indices_2[i], "on_attester_slashing: attesting_indices must be sorted and unique");
+    if (n1 == 0 || n2 == 0) return B2_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_a, (size_t)n1 * 4)) || (rc = ensure(ctx, ctx->in_b, (size_t)n2 * 4))) return rc;
+    CK(cudaMemcpyAsync(ctx->in_a.p, indices_1, (size_t)n1 * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_b.p, indices_2, (size_t)n2 * 4, cudaMemcpyHostToDevice, s));
+    k_mark_equivocating<<<blocks_for(n1, 128), 128, 0, s>>>((const uint32_t*)ctx->in_a.p, n1, (const uint32_t*)ctx->in_b.p, n2, ctx->n_val, ctx->d_equiv);
+    CKL(ctx);
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------------------------------ block tree
 int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, const uint8_t* root32, const uint8_t* leaf_viable, uint32_t n) {
     REQUIRE(ctx && parent && slot && root32 && leaf_viable && n > 0, "tree_load: bad arguments");
@@ -872,10 +918,12 @@ int b2_vote_weights_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, void* stream) {
     const size_t bins_bytes = (size_t)ctx->n_blocks * 8;
     if (bins_bytes <= 200 * 1024) {
         k_ghost_votes_smem<<<ctx->n_sm, 1024, bins_bytes, s>>>(ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff,
-                                                              ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder);
+                                                              ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder, ctx->fc_min_key, 1u,
+                                                              ctx->fc_exclude_slashed ? 3u : 1u);
     } else {
         k_ghost_votes<<<blocks_for(ctx->n_val, 256), 256, 0, s>>>(ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff,
-                                                                  ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder);
+                                                                  ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder, ctx->fc_min_key, 1u,
+                                                              ctx->fc_exclude_slashed ? 3u : 1u);
     }
     CKL(ctx);
     CK(cudaEventRecord(ctx->ev_votes_done, s));

@@ -390,13 +390,13 @@ __global__ void __launch_bounds__(128) k_lmd_phase2(const uint32_t* __restrict__
 __global__ void __launch_bounds__(256) k_ghost_votes(uint64_t n, const unsigned long long* __restrict__ lmd_key,
                                                       const uint32_t* __restrict__ lmd_block, const uint8_t* __restrict__ equiv,
                                                       const uint8_t* __restrict__ flags, const uint64_t* __restrict__ eff,
-                                                      const uint32_t* __restrict__ pre, uint32_t n_blocks, unsigned long long* votes) {
+                                                      const uint32_t* __restrict__ pre, uint32_t n_blocks, unsigned long long* votes, unsigned long long min_key, uint32_t flag_need, uint32_t flag_mask) {
     uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool on = v < n;
     uint32_t b = 0xffffffffu;
     unsigned long long bal = 0;
     if (on) {
-        on = lmd_key[v] != 0 && !equiv[v] && (flags[v] & 1);
+        on = lmd_key[v] != 0 && lmd_key[v] >= min_key && !equiv[v] && ((flags[v] & flag_mask) == flag_need);
         if (on) {
             uint32_t blk = lmd_block[v];
             on = blk < n_blocks;
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(256) k_ghost_votes(uint64_t n, const unsigned 
 __global__ void __launch_bounds__(1024) k_ghost_votes_smem(uint64_t n, const unsigned long long* __restrict__ lmd_key,
                                                             const uint32_t* __restrict__ lmd_block, const uint8_t* __restrict__ equiv,
                                                             const uint8_t* __restrict__ flags, const uint64_t* __restrict__ eff,
-                                                            const uint32_t* __restrict__ pre, uint32_t n_blocks, unsigned long long* votes) {
+                                                            const uint32_t* __restrict__ pre, uint32_t n_blocks, unsigned long long* votes, unsigned long long min_key, uint32_t flag_need, uint32_t flag_mask) {
     extern __shared__ unsigned long long bins[];
     for (uint32_t i = threadIdx.x; i < n_blocks; i += blockDim.x) bins[i] = 0;
     __syncthreads();
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(1024) k_ghost_votes_smem(uint64_t n, const uns
         uint32_t b = 0xffffffffu;
         unsigned long long bal = 0;
         if (on) {
-            on = lmd_key[v] != 0 && !equiv[v] && (flags[v] & 1);
+            on = lmd_key[v] != 0 && lmd_key[v] >= min_key && !equiv[v] && ((flags[v] & flag_mask) == flag_need);
             if (on) {
                 uint32_t blk = lmd_block[v];
                 on = blk < n_blocks;
@@ -818,5 +818,24 @@ __global__ void __launch_bounds__(128) k_part_phase3(const uint32_t* __restrict_
                 }
             if (won) atomicOr(&part_words[v >> 2], won << (8 * (v & 3)));
         }
+}
+}  // namespace b2
+
+// ------------------------------------------------------------------------------------------ fork-choice variants
+// on_attester_slashing (/root/reference/pos-evolution.md:1447-1461): the validators in BOTH attesting-index lists become
+// equivocating (Store.equivocating_indices, :897) and stop counting in get_weight (:1411-1413).  One thread per element of the
+// first (sorted) list, binary search in the second.
+namespace b2 {
+__global__ void __launch_bounds__(128) k_mark_equivocating(const uint32_t* __restrict__ idx1, uint32_t n1, const uint32_t* __restrict__ idx2, uint32_t n2,
+                                                            uint64_t n_val, uint8_t* equiv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const uint32_t v = idx1[i];
+    uint32_t lo = 0, hi = n2;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (idx2[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n2 && idx2[lo] == v && v < n_val) equiv[v] = 1;
 }
 }  // namespace b2

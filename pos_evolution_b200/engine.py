@@ -217,6 +217,14 @@ class Engine:
                                                   int(increment), int(base_reward_per_increment), _p(num)))
         return num
 
+    def set_fork_choice_params(self, min_vote_epoch: int = 0, exclude_slashed: bool = False):
+        self._ck(self.lib.b2_set_fork_choice_params(self.h, int(min_vote_epoch), 1 if exclude_slashed else 0))
+
+    def on_attester_slashing(self, indices_1, indices_2):
+        """Store.equivocating_indices |= set(indices_1) & set(indices_2)   (pos-evolution.md:1459-1461); both lists sorted."""
+        a, b = _c(indices_1, np.uint32), _c(indices_2, np.uint32)
+        self._ck(self.lib.b2_on_attester_slashing(self.h, _p(a), a.shape[0], _p(b), b.shape[0]))
+
     def tree_load(self, parent, slot, roots32, leaf_viable):
         parent, slot = _c(parent, np.uint32), _c(slot, np.uint64)
         roots = _c(roots32, np.uint8).reshape(-1, 32)

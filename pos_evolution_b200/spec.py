@@ -90,6 +90,12 @@ class IndexedAttestation:
     signature: bytes
 
 
+@dataclass
+class AttesterSlashing:                # pos-evolution.md:1160-1162
+    attestation_1: "IndexedAttestation"
+    attestation_2: "IndexedAttestation"
+
+
 @dataclass(frozen=True)
 class LatestMessage:                   # :287-289
     epoch: int
@@ -517,6 +523,21 @@ class Spec:
         indexed = self.get_indexed_attestation(target_state, attestation)
         assert self.is_valid_indexed_attestation(target_state, indexed)
         self.update_latest_messages(store, indexed.attesting_indices, attestation)
+
+    @staticmethod
+    def is_slashable_attestation_data(data_1, data_2):                         # :1134-1143
+        double_vote = data_1 != data_2 and data_1.target.epoch == data_2.target.epoch
+        surround_vote = data_1.source.epoch < data_2.source.epoch and data_2.target.epoch < data_1.target.epoch
+        return double_vote or surround_vote
+
+    def on_attester_slashing(self, store, attester_slashing):                  # :1447-1461
+        a1, a2 = attester_slashing.attestation_1, attester_slashing.attestation_2
+        assert self.is_slashable_attestation_data(a1.data, a2.data)
+        state = store.block_states[store.justified_checkpoint.root]
+        ok = self.are_valid_indexed_attestations(state, [a1, a2])              # both signatures in one GPU batch
+        assert ok[0] and ok[1]
+        for index in set(a1.attesting_indices).intersection(a2.attesting_indices):
+            store.equivocating_indices.add(index)
 
     def _store_arrays(self, store):
         """Store (dicts) -> the array form of include/b200pos.h: blocks below the justified root in topological order."""

@@ -135,3 +135,34 @@ def test_gpu_signing_roots_match_oracle(eng):
     one = eng.signing_roots(np.frombuffer(b"".join(ser), dtype=np.uint8), np.frombuffer(doms[0], dtype=np.uint8))
     for i in range(n):
         assert bytes(one[i]) == OS.Spec.compute_signing_root(datas[i], doms[0])
+
+
+def test_fork_choice_variants_expiry_slashed_equivocation(eng):
+    """vote expiry (min epoch), v1.3 slashed exclusion, on_attester_slashing marking -- vs numpy."""
+    n_val, n_blk = 6000, 400
+    parent, slot, roots, leaf_viable = scenarios.fork_tree(n_blk, 11)
+    msg_block, has_msg, equiv, active, eff = scenarios.votes(n_val, n_blk, 11)
+    rng = np.random.default_rng(11)
+    epochs = rng.integers(1, 9, size=n_val).astype(np.uint64)
+    slashed = (rng.random(n_val) < 0.05).astype(np.uint8)
+    flags = (active | (slashed << 1)).astype(np.uint8)
+    _registry(eng, n_val, eff, flags)
+    eng.tree_load(parent, slot, roots, leaf_viable)
+    eng.latest_messages_load(epochs, msg_block, has_msg, equiv)
+    keep = fast.ghost_viable(parent, leaf_viable)
+    for min_epoch, excl in ((0, False), (5, False), (0, True), (7, True)):
+        eng.set_fork_choice_params(min_epoch, excl)
+        hm = has_msg & (epochs >= min_epoch).astype(np.uint8)
+        act = active & (1 - slashed) if excl else active
+        w_ref = fast.ghost_weights(parent, msg_block, hm, eff, act, equiv, -1, 0)
+        assert np.array_equal(eng.get_weights(), w_ref)
+        assert eng.get_head(0) == fast.ghost_head(parent, roots, keep, w_ref, 0)
+    eng.set_fork_choice_params(0, False)
+    a1 = np.unique(rng.integers(0, n_val, size=500)).astype(np.uint32)
+    a2 = np.unique(rng.integers(0, n_val, size=500)).astype(np.uint32)
+    eng.on_attester_slashing(a1, a2)
+    eq2 = equiv.copy()
+    eq2[np.intersect1d(a1, a2)] = 1
+    assert len(np.intersect1d(a1, a2)) > 0
+    w_ref = fast.ghost_weights(parent, msg_block, has_msg, eff, active, eq2, -1, 0)
+    assert np.array_equal(eng.get_weights(), w_ref)

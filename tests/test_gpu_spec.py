@@ -153,3 +153,27 @@ def test_get_head_and_weight_match_oracle(env):
     bad = scenarios.make_attestation(ospec, ostate2, 8, 0, corrupt="flip_bit")
     with pytest.raises(AssertionError):
         pspec.on_attestation(pstore, _to_product(PS, bad))
+
+
+def test_on_attester_slashing_marks_equivocators(env):
+    """on_attester_slashing (:1447-1461): two conflicting, correctly signed indexed attestations -> the common signers become
+    equivocating and stop counting in get_weight; an unsigned/invalid slashing is rejected and leaves the store untouched."""
+    ospec, ostate, pspec, PS, PB, pks = env
+    pstate = _state_to_product(PS, ostate)
+    com = ospec.get_beacon_committee(ostate, 8, 0)
+    att1 = scenarios.make_attestation(ospec, ostate, 8, 0, head_root=b"\x01" * 32)
+    att2 = scenarios.make_attestation(ospec, ostate, 8, 0, head_root=b"\x02" * 32)          # same target epoch, different data: double vote
+    ia = [PS.IndexedAttestation(sorted(com), _to_product(PS, a.data), a.signature) for a in (att1, att2)]
+    just = PS.Checkpoint(1, b"\x07" * 32)
+    store = PS.Store(0, 0, just, just, just, PS.ZERO32, set())
+    store.block_states[just.root] = pstate
+    pspec.on_attester_slashing(store, PS.AttesterSlashing(ia[0], ia[1]))
+    assert store.equivocating_indices == set(com)
+    store2 = PS.Store(0, 0, just, just, just, PS.ZERO32, set())
+    store2.block_states[just.root] = pstate
+    with pytest.raises(AssertionError):                     # not slashable: identical data
+        pspec.on_attester_slashing(store2, PS.AttesterSlashing(ia[0], ia[0]))
+    bad = PS.IndexedAttestation(sorted(com), ia[1].data, ia[0].signature)                   # signature of the other message
+    with pytest.raises(AssertionError):
+        pspec.on_attester_slashing(store2, PS.AttesterSlashing(ia[0], bad))
+    assert store2.equivocating_indices == set()
