@@ -218,7 +218,7 @@ def run_gpu(args):
         pg = dist.group.WORLD
     eng = Engine(local)
     W = build_world(eng, rank, np, PS)
-    ep = EpochProcessor(eng, N_AGG, N_VAL, COMMITTEE_SIZE // 8, N_BLOCKS, process_group=pg, device=dev)
+    ep = EpochProcessor(eng, N_AGG, N_VAL, COMMITTEE_SIZE // 8, N_BLOCKS, process_group=pg, device=dev, depth=args.depth)
     ep.set_committees(W["members"], W["off"])
     bits_np = np.full((N_AGG, COMMITTEE_SIZE // 8), 0xFF, dtype=np.uint8)
     blk_np = (N_BLOCKS - 1 - (np.arange(N_AGG) % 64)).astype(np.int32)
@@ -230,7 +230,7 @@ def run_gpu(args):
     h_sigs = torch.as_tensor(W["sigs"]).pin_memory()
     h_bits = torch.as_tensor(bits_np).pin_memory()
     h_msgs = torch.as_tensor(W["msgs"]).pin_memory()
-    h_epochs = [torch.full((N_AGG,), 1000, dtype=torch.int64).pin_memory() for _ in range(2)]
+    h_epochs = [torch.full((N_AGG,), 1000, dtype=torch.int64).pin_memory() for _ in range(5)]
     host_epoch_counter = [0]
     h_blk = torch.as_tensor(blk_np).pin_memory()
     boost_idx, boost = N_BLOCKS - 1, W["boost"]
@@ -246,28 +246,27 @@ def run_gpu(args):
         return ep.process_epoch_dev(d_sigs, d_bits, d_msgs, d_epoch, d_blk, 0, boost_idx, boost)
 
     def run_pipelined_dev(n):
-        """n epochs through the two-slot software pipeline; every epoch's result is collected inside the call."""
+        """n epochs through the software pipeline; every epoch's result is complete (for the current stream) when this returns."""
         results = []
         for _ in range(n):
             d_epoch.add_(1)
             t = ep.submit_dev(d_sigs, d_bits, d_msgs, d_epoch, d_blk, 0, boost_idx, boost)
             if t is not None:
                 results.append(t)
-        results.append(ep.drain())
+        results.extend(ep.drain())
         return results
 
     def run_pipelined_host(n):
-        results, prev = [], None
+        results = []
         for _ in range(n):
-            if prev is not None:
-                results.append(prev.wait())            # host blocks on epoch k-2's D2H while epoch k-1 is in flight
             host_epoch_counter[0] += 1
-            he = h_epochs[host_epoch_counter[0] & 1]   # a pinned buffer is rewritten only after the epoch that last read it has completed
+            he = h_epochs[host_epoch_counter[0] % len(h_epochs)]   # a pinned buffer is rewritten only after the epoch that read it has completed
             he.fill_(1000 + host_epoch_counter[0])
-            prev = ep.submit_host(h_sigs, h_bits, h_msgs, he, h_blk, 0, boost_idx, boost)
-        if prev is not None:
-            results.append(prev.wait())
-        results.append(ep.drain().wait())
+            t = ep.submit_host(h_sigs, h_bits, h_msgs, he, h_blk, 0, boost_idx, boost)
+            if t is not None:
+                results.append(t.wait())               # host blocks on the D2H of the epoch submitted depth-1 calls ago
+        for t in ep.drain():
+            results.append(t.wait())
         return results
 
     # ---- warm-up, correctness gate: every aggregate must verify (synchronous and pipelined forms)
@@ -335,6 +334,24 @@ def run_gpu(args):
     torch.cuda.synchronize()
     ms_verify = kv0.elapsed_time(kv1) / reps
 
+    ms_overlap = None
+    if args.probe_overlap:
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+        ks0.record()
+        for _ in range(reps):
+            s1.wait_stream(torch.cuda.current_stream())
+            s2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s1):
+                eng.aggregate_dev(d_sigs, ep.d_off, ep.d_agg_sig[1], ep.d_agg_status[1])
+            with torch.cuda.stream(s2):
+                eng.fast_aggregate_verify_dev(ep.d_members, ep.d_off, d_bits, d_msgs, ep.d_agg_sig[0], ep.d_ok[0])
+            torch.cuda.current_stream().wait_stream(s1)
+            torch.cuda.current_stream().wait_stream(s2)
+        ks1.record()
+        torch.cuda.synchronize()
+        ms_overlap = ks0.elapsed_time(ks1) / reps
+
     # ---- get_head latency: C-ABI call incl. D2H of the head index
     lat = []
     for i in range(250):
@@ -374,13 +391,14 @@ def run_gpu(args):
             "ms_per_step": ms_dev, "ms_per_step_unpipelined": ms_sync, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (381-bit Fp, Montgomery)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "validators_per_rank": N_VAL, "aggregates_per_rank": N_AGG, "parallelism": "validators sharded x%d, one u64[10000] all-reduce" % world,
-                       "pipelining": "two-slot software pipeline: epoch k+1's signature decompression overlaps epoch k's pairing tail; all K results complete inside the timed region",
+                       "pipeline_depth": args.depth, "pipelining": "software pipeline over pipeline_depth slots: epoch k+1's signature decompression overlaps the pairing tails of epochs k and k-1; all K results complete inside the timed region",
                        "l2": "per-step working set ~0.5 GB (signatures 101 MB + decompressed points 201 MB + registry 101 MB) > 126 MB L2"},
             "e2e": {"value": world * N_VAL / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": ep.h2d_bytes, "d2h_bytes_per_step": ep.d2h_bytes},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "get_head_p50_us": p50, "get_head_p99_us": p99, "head_index": head0,
-            "stage_ms": {"bls_aggregate_2^20_sigs": ms_agg, "fast_aggregate_verify_2048": ms_verify},
+            "stage_ms": {"bls_aggregate_2^20_sigs": ms_agg, "fast_aggregate_verify_2048": ms_verify,
+                         **({"aggregate_and_verify_concurrent": ms_overlap} if ms_overlap is not None else {})},
             "roofline": {"bound": "hbm", "kernel": "bls.Aggregate (k_g2_decompress + k_g2_segment_sum)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES_K3, "peak_source": peak_src,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_g2_decompress (profiles/)",
@@ -422,6 +440,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=3, help="epochs in flight in the software pipeline (2..4)")
+    ap.add_argument("--probe-overlap", action="store_true",
+                    help="also time bls.Aggregate and FastAggregateVerify running concurrently on two streams (diagnostic)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -155,13 +155,17 @@ int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const u
 int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                  uint32_t bits_stride, const uint8_t* d_msg32, const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg,
                  uint64_t n_sig, uint8_t* d_agg_sig96, int32_t* d_agg_status, uint8_t* d_ok_out, void* stream);
-/* Software-pipelined form of b2_epoch_dev (two slots, 0/1 alternating).  Per epoch k with slot = k & 1:
- *   b2_epoch_start_dev(slot)  on `stream`: forks the pubkey/hash half, decompresses and segment-sums the signatures;
- *   [finish epoch k-1: b2_epoch_wait_dev(slot ^ 1, stream); b2_vote_weights_dev; all-reduce; b2_head_from_votes_dev]
- *   b2_epoch_tail_dev(slot)   on the context's own high-priority stream: inversion + compress, subgroup check, second Miller
- *                             loop, final exponentiation, update_latest_messages.  Its outputs (aggregate signatures, verdicts)
- *                             are valid for a stream only after b2_epoch_wait_dev(slot, that stream).
- * The latency-bound tail of epoch k thereby overlaps with the grid-filling signature decompression of epoch k+1. */
+/* Software-pipelined form of b2_epoch_dev.  Epoch k uses slot = k mod depth, depth <= B2_EPOCH_SLOTS:
+ *   b2_epoch_start_dev(slot)  on `stream`: forks the pubkey/hash half, decompresses and segment-sums the signatures (waits until
+ *                             the slot's previous tail has drained);
+ *   b2_epoch_tail_dev(slot)   on the slot's own high-priority stream: inversion + compress, subgroup check, second Miller loop,
+ *                             final exponentiation, update_latest_messages (applied in epoch order).  Its outputs (aggregate
+ *                             signatures, verdicts, the LMD table) are valid for a stream only after b2_epoch_wait_dev(slot, it);
+ *   fork choice of epoch k    b2_epoch_wait_dev(slot, s); b2_vote_weights_dev(s); all-reduce; b2_head_from_votes_dev(s) -- enqueue it
+ *                             before the tail of epoch k+1, whose LMD update waits for the vote scatter issued before it.
+ * The latency-bound tails of epochs k, k-1, .. thereby overlap with each other and with the grid-filling signature decompression of
+ * epoch k+1: under that contention one tail takes longer than one decompression, so depth 3 is what keeps the multiply pipe busy. */
+#define B2_EPOCH_SLOTS 4
 int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                        uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, void* stream);
 int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,

@@ -20,14 +20,15 @@ struct dbuf {
 struct vslot {
     dbuf haff, hflag, pkjac, pkst, saff, sflag, f, sumjac;
     cudaEvent_t ev_join0 = nullptr, ev_join1 = nullptr, ev_seg = nullptr, ev_tail_done = nullptr;
+    cudaStream_t s_tail = nullptr;      // the slot's own tail stream: tails of consecutive epochs overlap each other
 };
 
 struct b2_ctx {
     int device = 0;
     int n_sm = 148;
-    cudaStream_t s_main = nullptr, s_aux[2] = {nullptr, nullptr}, s_tail = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_votes_done = nullptr;
-    vslot slot[2];
+    cudaStream_t s_main = nullptr, s_aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_votes_done = nullptr, ev_lmd_done = nullptr;
+    vslot slot[B2_EPOCH_SLOTS];
     char err[512] = {0};
     uint64_t launches = 0;
     // registry
@@ -41,6 +42,12 @@ struct b2_ctx {
     uint32_t* d_lmd_block = nullptr;
     uint8_t* d_equiv = nullptr;
     // fork-choice variants: votes older than fc_min_key (epoch << 32) expire; v1.3 get_weight skips slashed validators
+    // threads per block of the thread-per-aggregate kernels when they run under the epoch pipeline (see launch_miller)
+    unsigned tail_block = 128;
+    int pairing_form = 0;      // 0: team kernels for the synchronous calls, thread-per-aggregate under the pipeline; 1: always team; 2: always thread
+    // threads per block of k_g2_decompress: its blocks fill the register file, so a smaller block is what a pairing warp of the
+    // previous epoch displaces when the two overlap
+    unsigned dec_block = 128;
     unsigned long long fc_min_key = 0;
     int fc_exclude_slashed = 0;
     // epoch participation flags (0 = current, 1 = previous) and the per-(validator, flag) election table
@@ -123,16 +130,26 @@ int b2_init(int device, b2_ctx** out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaError_t e = cudaStreamCreateWithPriority(&ctx->s_main, cudaStreamNonBlocking, prio_lo);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithPriority(&ctx->s_aux[i], cudaStreamNonBlocking, prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->s_tail, cudaStreamNonBlocking, prio_hi);
+    for (int i = 0; i < B2_EPOCH_SLOTS && e == cudaSuccess; i++) e = cudaStreamCreateWithPriority(&ctx->slot[i].s_tail, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_lmd_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_votes_done, cudaEventDisableTiming);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    for (int i = 0; i < B2_EPOCH_SLOTS && e == cudaSuccess; i++) {
         cudaEvent_t* evs[4] = {&ctx->slot[i].ev_join0, &ctx->slot[i].ev_join1, &ctx->slot[i].ev_seg, &ctx->slot[i].ev_tail_done};
         for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(evs[k], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_votes_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     ctx->n_sm = prop.multiProcessorCount;
+    if (const char* e = getenv("B2_TAIL_BLOCK")) {          // tuning knob (32/64/128); the default is the measured best
+        unsigned v = (unsigned)atoi(e);
+        if (v == 32 || v == 64 || v == 128) ctx->tail_block = v;
+    }
+    if (const char* e = getenv("B2_PAIRING_FORM")) ctx->pairing_form = !strcmp(e, "team") ? 1 : (!strcmp(e, "thread") ? 2 : 0);
+    if (const char* e = getenv("B2_DEC_BLOCK")) {
+        unsigned v = (unsigned)atoi(e);
+        if (v == 32 || v == 64 || v == 128) ctx->dec_block = v;
+    }
     if (e != cudaSuccess) {
         delete ctx;
         return B2_ECUDA;
@@ -155,7 +172,7 @@ void b2_destroy(b2_ctx* ctx) {
                     &ctx->in_e, &ctx->in_f, &ctx->in_g, &ctx->out_a, &ctx->out_b, &ctx->sc_shuf, &ctx->sc_pivot};
     for (dbuf* b : bufs)
         if (b->p) cudaFree(b->p);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < B2_EPOCH_SLOTS; i++) {
         vslot& V = ctx->slot[i];
         dbuf* vb[] = {&V.haff, &V.hflag, &V.pkjac, &V.pkst, &V.saff, &V.sflag, &V.f, &V.sumjac};
         for (dbuf* b : vb)
@@ -163,10 +180,12 @@ void b2_destroy(b2_ctx* ctx) {
         cudaEvent_t evs[4] = {V.ev_join0, V.ev_join1, V.ev_seg, V.ev_tail_done};
         for (cudaEvent_t ev : evs)
             if (ev) cudaEventDestroy(ev);
-        if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
+        if (V.s_tail) cudaStreamDestroy(V.s_tail);
     }
+    for (int i = 0; i < 2; i++)
+        if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
-    if (ctx->s_tail) cudaStreamDestroy(ctx->s_tail);
+    if (ctx->ev_lmd_done) cudaEventDestroy(ctx->ev_lmd_done);
     if (ctx->ev_votes_done) cudaEventDestroy(ctx->ev_votes_done);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
@@ -294,7 +313,7 @@ static int aggregate_front(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, const 
         (rc = ensure(ctx, V.sumjac, (size_t)n_seg * 288)))
         return rc;
     if (n_sig) {
-        k_g2_decompress<<<blocks_for(n_sig, 128), 128, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p);
+        k_g2_decompress<<<blocks_for(n_sig, ctx->dec_block), ctx->dec_block, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p);
         CKL(ctx);
     }
     k_g2_segment_sum<<<n_seg, 32, 0, s>>>((const uint32_t*)ctx->sc_g2aff.p, (const uint8_t*)ctx->sc_g2st.p, d_seg_off, n_seg,
@@ -302,10 +321,11 @@ static int aggregate_front(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, const 
     CKL(ctx);
     return B2_OK;
 }
-static int aggregate_finish(b2_ctx* ctx, vslot& V, uint32_t n_seg, uint8_t* d_out96, const int32_t* d_seg_status, bool handoff, cudaStream_t s) {
+static int aggregate_finish(b2_ctx* ctx, vslot& V, uint32_t n_seg, uint8_t* d_out96, const int32_t* d_seg_status, bool handoff, cudaStream_t s,
+                            unsigned tb = 32) {
     int rc;
     if (handoff && ((rc = ensure(ctx, V.saff, (size_t)n_seg * 192)) || (rc = ensure(ctx, V.sflag, n_seg)))) return rc;
-    k_g2_finish<<<blocks_for(n_seg, 32), 32, 0, s>>>((const uint32_t*)V.sumjac.p, d_seg_status, n_seg, d_out96,
+    k_g2_finish<<<blocks_for(n_seg, tb), tb, 0, s>>>((const uint32_t*)V.sumjac.p, d_seg_status, n_seg, d_out96,
                                                     handoff ? (uint32_t*)V.saff.p : nullptr, handoff ? (uint8_t*)V.sflag.p : nullptr);
     CKL(ctx);
     return B2_OK;
@@ -365,13 +385,15 @@ struct pk_source {
 // Two forms of K5/K6.  `team`: three lanes per pairing -- shortest critical path, used when the caller waits for the result
 // (synchronous entry points).  Thread-per-item: 2.7x longer, but ~40 % fewer warp instructions in total -- used by the pipelined
 // epoch API, where the latency hides behind the next epoch's decompression and only the stolen multiply-pipe time counts.
+static inline bool use_team(const b2_ctx* ctx, bool team) { return ctx->pairing_form == 0 ? team : ctx->pairing_form == 1; }
 static int launch_miller(b2_ctx* ctx, vslot& V, uint32_t n_agg, int mode, bool team, cudaStream_t s) {
+    team = use_team(ctx, team);
     if (team) {
         k_miller_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, s>>>(
             (const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p, (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p,
             (const uint8_t*)V.sflag.p, n_agg, (uint32_t*)V.f.p, mode);
     } else {
-        k_miller<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p,
+        k_miller<<<blocks_for(n_agg, ctx->tail_block), ctx->tail_block, 0, s>>>((const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p,
                                                       (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p, (const uint8_t*)V.sflag.p, n_agg,
                                                       (uint32_t*)V.f.p, mode);
     }
@@ -379,11 +401,12 @@ static int launch_miller(b2_ctx* ctx, vslot& V, uint32_t n_agg, int mode, bool t
     return B2_OK;
 }
 static int launch_final(b2_ctx* ctx, vslot& V, uint32_t n_agg, uint8_t* d_ok, bool team, cudaStream_t s) {
+    team = use_team(ctx, team);
     if (team) {
         k_final_team<<<blocks_for(n_agg, B2_TEAMS_PER_WARP), 32, B2_TEAM_SMEM, s>>>((const uint32_t*)V.f.p, (const uint8_t*)V.pkst.p,
                                                                                   (const uint8_t*)V.sflag.p, n_agg, d_ok);
     } else {
-        k_final_verdict<<<blocks_for(n_agg, 32), 32, 0, s>>>((const uint32_t*)V.f.p, (const uint8_t*)V.pkst.p, (const uint8_t*)V.sflag.p, n_agg, d_ok);
+        k_final_verdict<<<blocks_for(n_agg, ctx->tail_block), ctx->tail_block, 0, s>>>((const uint32_t*)V.f.p, (const uint8_t*)V.pkst.p, (const uint8_t*)V.sflag.p, n_agg, d_ok);
     }
     CKL(ctx);
     return B2_OK;
@@ -398,7 +421,8 @@ static int verify_fork(b2_ctx* ctx, vslot& V, const pk_source& P, const uint8_t*
     CK(cudaEventRecord(ctx->ev_fork, s));
     CK(cudaStreamWaitEvent(ctx->s_aux[0], ctx->ev_fork, 0));
     CK(cudaStreamWaitEvent(ctx->s_aux[1], ctx->ev_fork, 0));
-    k_hash_to_g2<<<blocks_for(n_agg, 32), 32, 0, ctx->s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)V.haff.p, (uint8_t*)V.hflag.p);
+    const unsigned tb = team ? 32u : ctx->tail_block;
+    k_hash_to_g2<<<blocks_for(n_agg, tb), tb, 0, ctx->s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)V.haff.p, (uint8_t*)V.hflag.p);
     CKL(ctx);
     CK(cudaEventRecord(V.ev_join0, ctx->s_aux[0]));
     if (P.d_pk48) {
@@ -454,7 +478,7 @@ static int epoch_start(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint
                        uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, cudaStream_t s, bool team) {
     vslot& V = ctx->slot[slot];
     int rc;
-    CK(cudaStreamWaitEvent(s, V.ev_tail_done, 0));      // the slot's previous user (two epochs ago) must have drained
+    CK(cudaStreamWaitEvent(s, V.ev_tail_done, 0));      // the slot's previous user (B2_EPOCH_SLOTS-or-fewer epochs ago) must have drained
     pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
     if ((rc = verify_fork(ctx, V, P, d_msg32, n_agg, s, team))) return rc;
     if ((rc = aggregate_front(ctx, V, d_sig96, d_off, n_agg, n_sig, d_agg_status, s))) return rc;
@@ -467,10 +491,12 @@ static int epoch_tail(b2_ctx* ctx, int slot, const uint32_t* d_members, const ui
     vslot& V = ctx->slot[slot];
     int rc;
     CK(cudaStreamWaitEvent(t, V.ev_seg, 0));
-    if ((rc = aggregate_finish(ctx, V, n_agg, d_agg_sig96, d_agg_status, true, t))) return rc;
+    if ((rc = aggregate_finish(ctx, V, n_agg, d_agg_sig96, d_agg_status, true, t, team ? 32u : ctx->tail_block))) return rc;
     if ((rc = verify_main(ctx, V, nullptr, n_agg, d_ok_out, t, team))) return rc;
     CK(cudaStreamWaitEvent(t, ctx->ev_votes_done, 0));  // do not move the LMD table under a vote scatter that is still reading it
+    CK(cudaStreamWaitEvent(t, ctx->ev_lmd_done, 0));    // latest messages are applied in epoch order even when tails overlap
     if ((rc = b2_latest_messages_update_dev(ctx, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_ok_out, n_agg, t))) return rc;
+    CK(cudaEventRecord(ctx->ev_lmd_done, t));
     CK(cudaEventRecord(V.ev_tail_done, t));
     return B2_OK;
 }
@@ -488,11 +514,12 @@ int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members,
     return epoch_tail(ctx, 0, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, n_agg, d_agg_sig96, d_agg_status, d_ok_out, s, true);
 }
 
-// Pipelined form: call start(slot), then [finish the previous epoch: b2_epoch_wait_dev(other slot) + vote weights + head], then
-// tail(slot); alternate slot = 0, 1, 0, ...  The tail runs on the context's own high-priority stream.
+// Pipelined form: per epoch k, slot = k mod depth (depth <= B2_EPOCH_SLOTS): start(slot) on the caller's stream, tail(slot) on the
+// slot's own high-priority stream, then the fork choice of the epoch on any stream after b2_epoch_wait_dev(slot, stream).  Tails of
+// consecutive epochs overlap each other and the following decompressions; latest messages are still applied in epoch order.
 int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                        uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, void* stream) {
-    REQUIRE(ctx && (slot == 0 || slot == 1) && d_sig96 && d_members && d_off && d_bits && d_msg32 && d_agg_status && n_agg > 0 && bits_stride > 0,
+    REQUIRE(ctx && slot >= 0 && slot < B2_EPOCH_SLOTS && d_sig96 && d_members && d_off && d_bits && d_msg32 && d_agg_status && n_agg > 0 && bits_stride > 0,
             "epoch_start_dev: bad arguments");
     REQUIRE(ctx->n_val > 0, "epoch_start_dev: registry not loaded");
     CK(cudaSetDevice(ctx->device));
@@ -501,14 +528,14 @@ int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint
 int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
                       const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
                       uint8_t* d_ok_out) {
-    REQUIRE(ctx && (slot == 0 || slot == 1) && d_members && d_off && d_bits && d_target_epoch && d_block_idx && d_agg_sig96 && d_agg_status && d_ok_out &&
+    REQUIRE(ctx && slot >= 0 && slot < B2_EPOCH_SLOTS && d_members && d_off && d_bits && d_target_epoch && d_block_idx && d_agg_sig96 && d_agg_status && d_ok_out &&
                 n_agg > 0 && bits_stride > 0, "epoch_tail_dev: bad arguments");
     CK(cudaSetDevice(ctx->device));
     return epoch_tail(ctx, slot, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, n_agg, d_agg_sig96, d_agg_status, d_ok_out,
-                      ctx->s_tail, false);
+                      ctx->slot[slot].s_tail, false);
 }
 int b2_epoch_wait_dev(b2_ctx* ctx, int slot, void* stream) {
-    REQUIRE(ctx && (slot == 0 || slot == 1), "epoch_wait_dev: bad arguments");
+    REQUIRE(ctx && slot >= 0 && slot < B2_EPOCH_SLOTS, "epoch_wait_dev: bad arguments");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->slot[slot].ev_tail_done, 0));
     return B2_OK;

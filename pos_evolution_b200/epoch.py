@@ -9,59 +9,67 @@ One call processes a whole epoch of attestations for the validators this rank ow
 
 Two ways to drive it:
   * `process_epoch_dev` / `process_epoch_host`: synchronous in stream order, one epoch at a time;
-  * `submit_dev` / `submit_host` + `drain`: software-pipelined over two slots.  The signature decompression of
-    epoch k+1 (grid-filling, integer-pipe bound) overlaps with the latency-bound tail of epoch k (subgroup check,
-    second Miller loop, final exponentiation, LMD update) which runs on the library's own high-priority stream, and in
-    the host form the H2D copy of epoch k+1 overlaps with the compute of epoch k.  Results come back one call later.
+  * `submit_dev` / `submit_host` + `drain`: software-pipelined over `depth` slots (default 3).  The signature
+    decompression of epoch k+1 (grid-filling, integer-pipe bound) overlaps with the latency-bound tails of epochs k and
+    k-1 (subgroup check, second Miller loop, final exponentiation, LMD update; each on its slot's own high-priority
+    stream inside the library) and with their fork choice (on this object's fork-choice stream); in the host form the
+    H2D copy of epoch k+1 overlaps too.  Under that contention one tail takes longer than one decompression, which is
+    why two of them are kept in flight.  `submit_*` returns the ticket of the epoch submitted depth-1 calls earlier.
 
 Multi-GPU: validators (and with them committees / aggregates) are sharded across ranks with no data-path exchange
 until the vote weights: u64[n_blocks] direct votes are summed with one torch.distributed all_reduce (NCCL over NVLink;
 int64 two's-complement sum == u64 sum), after which every rank finishes get_head on its replica of the block tree.
 """
+import collections
+
 import torch
 
 from .engine import Engine
 
 
 class _Ticket:
-    """Result of one submitted epoch: verdict bytes + head index, valid after .wait()."""
+    """Result of one submitted epoch: verdict bytes + head index (+ the aggregate signatures on the device), valid after
+    .wait() and until `depth` further epochs have been submitted."""
 
-    def __init__(self, d_ok, d_head, h_ok=None, h_head=None, event=None):
-        self.d_ok, self.d_head, self.h_ok, self.h_head, self.event = d_ok, d_head, h_ok, h_head, event
+    def __init__(self, slot, d_ok, d_head, d_agg_sig, event, h_ok=None, h_head=None):
+        self.slot, self.d_ok, self.d_head, self.d_agg_sig, self.event, self.h_ok, self.h_head = slot, d_ok, d_head, d_agg_sig, event, h_ok, h_head
 
     def wait(self):
-        if self.event is not None:
-            self.event.synchronize()
-            return self.h_ok, int(self.h_head[0])
-        torch.cuda.current_stream().synchronize()
+        self.event.synchronize()
+        if self.h_ok is not None:
+            return self.h_ok.clone(), int(self.h_head[0])
         return self.d_ok, int(self.d_head[0])
 
 
 class EpochProcessor:
-    def __init__(self, engine: Engine, n_agg: int, n_sig: int, bits_stride: int, n_blocks: int, process_group=None, device=None):
+    def __init__(self, engine: Engine, n_agg: int, n_sig: int, bits_stride: int, n_blocks: int, process_group=None, device=None, depth: int = 3):
         self.eng = engine
         self.dev = device if device is not None else torch.device("cuda", engine.device)
         self.pg = process_group
         self.n_agg, self.n_sig, self.n_blocks = n_agg, n_sig, n_blocks
         d = self.dev
         cuda = self.dev.type == "cuda"
+        assert 2 <= depth <= 4, "depth must be 2..B2_EPOCH_SLOTS"
+        self.depth = S = depth
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=d)            # noqa: E731
-        self.d_agg_sig = [z((n_agg, 96), torch.uint8) for _ in range(2)]
-        self.d_agg_status = [z(n_agg, torch.int32) for _ in range(2)]
-        self.d_ok = [z(n_agg, torch.uint8) for _ in range(2)]
-        self.d_head = [z(1, torch.int32) for _ in range(2)]
+        self.d_agg_sig = [z((n_agg, 96), torch.uint8) for _ in range(S)]
+        self.d_agg_status = [z(n_agg, torch.int32) for _ in range(S)]
+        self.d_ok = [z(n_agg, torch.uint8) for _ in range(S)]
+        self.d_head = [z(1, torch.int32) for _ in range(S)]
         self.d_votes = z(n_blocks, torch.int64)
         # per-slot copies of everything the asynchronous tail / side streams read, and staging for the host entry points
-        self.s_sigs = [z((n_sig, 96), torch.uint8) for _ in range(2)]
-        self.s_bits = [z((n_agg, bits_stride), torch.uint8) for _ in range(2)]
-        self.s_msgs = [z((n_agg, 32), torch.uint8) for _ in range(2)]
-        self.s_epoch = [z(n_agg, torch.int64) for _ in range(2)]
-        self.s_blk = [z(n_agg, torch.int32) for _ in range(2)]
-        self.h_ok = [torch.zeros(n_agg, dtype=torch.uint8, pin_memory=cuda) for _ in range(2)]
-        self.h_head = [torch.zeros(1, dtype=torch.int32, pin_memory=cuda) for _ in range(2)]
+        self.s_sigs = [z((n_sig, 96), torch.uint8) for _ in range(S)]
+        self.s_bits = [z((n_agg, bits_stride), torch.uint8) for _ in range(S)]
+        self.s_msgs = [z((n_agg, 32), torch.uint8) for _ in range(S)]
+        self.s_epoch = [z(n_agg, torch.int64) for _ in range(S)]
+        self.s_blk = [z(n_agg, torch.int32) for _ in range(S)]
+        self.h_ok = [torch.zeros(n_agg, dtype=torch.uint8, pin_memory=cuda) for _ in range(S)]
+        self.h_head = [torch.zeros(1, dtype=torch.int32, pin_memory=cuda) for _ in range(S)]
         self.copy_stream = torch.cuda.Stream(device=d) if cuda else None
+        self.fc_stream = torch.cuda.Stream(device=d) if cuda else None
+        self.ev_fc = [None] * S       # per slot: fork choice (+ D2H) of the epoch that last used the slot
         self.k = 0
-        self._pending = None          # (slot, fork-choice args, host?) of the epoch whose tail is in flight
+        self._inflight = collections.deque()      # tickets of the submitted, not yet returned epochs
 
     def set_committees(self, members, off):
         """members u32[n_sig] (committee order), off u32[n_agg+1]; signature j belongs to member j."""
@@ -102,47 +110,48 @@ class EpochProcessor:
         return self.h_ok[s], int(self.h_head[s][0])
 
     # ------------------------------------------------------------------ pipelined form
-    def _finish_pending(self):
-        """Fork choice (and, for host submissions, the D2H of the results) of the epoch whose tail is in flight."""
-        if self._pending is None:
-            return None
-        slot, fc, host = self._pending
-        self._pending = None
-        self.eng.epoch_wait_dev(slot)
-        self._fork_choice(slot, *fc)
-        if not host:
-            return _Ticket(self.d_ok[slot], self.d_head[slot])
-        self.h_ok[slot].copy_(self.d_ok[slot], non_blocking=True)
-        self.h_head[slot].copy_(self.d_head[slot], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        return _Ticket(self.d_ok[slot], self.d_head[slot], self.h_ok[slot], self.h_head[slot], ev)
-
     def _submit(self, slot, d_sigs, d_bits, d_msgs, fc, host):
         e = self.eng
         e.epoch_start_dev(slot, d_sigs, self.d_members, self.d_off, d_bits, d_msgs, self.d_agg_status[slot])
-        done = self._finish_pending()                     # epoch k-1: after start(k) so that its wait does not stall the decompression
         e.epoch_tail_dev(slot, self.d_members, self.d_off, d_bits, self.s_epoch[slot], self.s_blk[slot], self.d_agg_sig[slot],
                          self.d_agg_status[slot], self.d_ok[slot])
-        self._pending = (slot, fc, host)
+        # fork choice of this epoch: on its own stream, enqueued BEFORE the next epoch's tail (whose LMD update waits for this scatter)
+        with torch.cuda.stream(self.fc_stream):
+            e.epoch_wait_dev(slot)
+            self._fork_choice(slot, *fc)
+            if host:
+                self.h_ok[slot].copy_(self.d_ok[slot], non_blocking=True)
+                self.h_head[slot].copy_(self.d_head[slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self.ev_fc[slot] = ev
+        self._inflight.append(_Ticket(slot, self.d_ok[slot], self.d_head[slot], self.d_agg_sig[slot], ev,
+                                      self.h_ok[slot] if host else None, self.h_head[slot] if host else None))
         self.k += 1
-        return done
+        return self._inflight.popleft() if len(self._inflight) >= self.depth else None
+
+    def _claim_slot(self, stream):
+        """`stream` is about to overwrite the slot's inputs/outputs: its previous epoch (tail and fork choice) must be done."""
+        slot = self.k % self.depth
+        self.eng.epoch_wait_dev(slot)                     # (on the current stream == `stream`)
+        if self.ev_fc[slot] is not None:
+            stream.wait_event(self.ev_fc[slot])
+        return slot
 
     def submit_dev(self, d_sigs, d_bits, d_msgs, d_target_epoch, d_block_idx, justified_idx=0, boost_idx=-1, boost_score=0):
-        """Enqueue one epoch (device-resident inputs, which must stay untouched until its ticket is returned).
-        Returns the ticket of the PREVIOUS epoch (None for the first call)."""
-        slot = self.k & 1
-        self.eng.epoch_wait_dev(slot)                     # the slot's previous tail must be done before its small inputs are replaced
+        """Enqueue one epoch (device-resident inputs, which must stay untouched until its ticket has been waited for).
+        Returns the ticket of the epoch submitted depth-1 calls earlier (None while the pipeline fills)."""
+        slot = self._claim_slot(torch.cuda.current_stream())
         self.s_epoch[slot].copy_(d_target_epoch)
         self.s_blk[slot].copy_(d_block_idx)
         return self._submit(slot, d_sigs, d_bits, d_msgs, (justified_idx, boost_idx, boost_score), False)
 
     def submit_host(self, h_sigs, h_bits, h_msgs, h_target_epoch, h_block_idx, justified_idx=0, boost_idx=-1, boost_score=0):
-        """Pinned host tensors in.  The H2D copies go on a separate stream so that they overlap with the previous epoch."""
-        slot = self.k & 1
+        """Pinned host tensors in (untouched until the returned-later ticket has been waited for).  The H2D copies go on a
+        separate stream so that they overlap with the epochs in flight."""
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(self.copy_stream):
-            self.eng.epoch_wait_dev(slot)                 # copy stream waits for the slot's previous tail (it reads bits/epoch/blk)
+            slot = self._claim_slot(self.copy_stream)
             self.s_sigs[slot].copy_(h_sigs, non_blocking=True)
             self.s_bits[slot].copy_(h_bits, non_blocking=True)
             self.s_msgs[slot].copy_(h_msgs, non_blocking=True)
@@ -154,8 +163,12 @@ class EpochProcessor:
         return self._submit(slot, self.s_sigs[slot], self.s_bits[slot], self.s_msgs[slot], (justified_idx, boost_idx, boost_score), True)
 
     def drain(self):
-        """Finish the last submitted epoch; returns its ticket."""
-        return self._finish_pending()
+        """Tickets of the epochs still in flight, oldest first; the current stream waits for all of them."""
+        out = list(self._inflight)
+        self._inflight.clear()
+        for t in out:
+            torch.cuda.current_stream().wait_event(t.event)
+        return out
 
     @property
     def h2d_bytes(self):

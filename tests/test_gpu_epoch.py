@@ -60,8 +60,9 @@ def _expected(pks, members, off, msgs, bits, sigs):
     return aggs, oks
 
 
-@pytest.mark.parametrize("mode", ["sync", "pipelined", "pipelined_host", "sync_host"])
-def test_epoch_pipeline_matches_oracle(mode):
+@pytest.mark.parametrize("mode,depth", [("sync", 3), ("pipelined", 2), ("pipelined", 3), ("pipelined", 4), ("pipelined_host", 3), ("pipelined_host", 2),
+                                        ("sync_host", 3)])
+def test_epoch_pipeline_matches_oracle(mode, depth):
     from pos_evolution_b200.engine import Engine
     from pos_evolution_b200.epoch import EpochProcessor
     pks, members, off, tree, eff = _world()
@@ -71,13 +72,18 @@ def test_epoch_pipeline_matches_oracle(mode):
     eng.tree_load(parent, slot, roots, leaf_viable)
     eng.latest_messages_reset()
     dev = torch.device("cuda", 0)
-    ep = EpochProcessor(eng, N_AGG, N_AGG * CSIZE, 1, N_BLK, device=dev)
+    ep = EpochProcessor(eng, N_AGG, N_AGG * CSIZE, 1, N_BLK, device=dev, depth=depth)
     ep.set_committees(members, off)
     rng = np.random.default_rng(3)
+
+    def collect(t):
+        ok, hd = t.wait()
+        tickets.append((ok.cpu().numpy().tolist(), hd, t.d_agg_sig.cpu().numpy().copy()))
+
     m_epoch, m_block, m_has = np.zeros(N_VAL, np.uint64), np.zeros(N_VAL, np.uint32), np.zeros(N_VAL, np.uint8)
     equiv, active = np.zeros(N_VAL, np.uint8), np.ones(N_VAL, np.uint8)
     expected, tickets, keep_alive = [], [], []
-    n_epochs = 4
+    n_epochs = 6
     for k in range(n_epochs):
         msgs, bits, sigs, te, bi = _epoch_inputs(k, members, off, rng)
         aggs, oks = _expected(pks, members, off, msgs, bits, sigs)
@@ -102,8 +108,7 @@ def test_epoch_pipeline_matches_oracle(mode):
             else:
                 t = ep.submit_host(*h)
                 if t is not None:
-                    ok, hd = t.wait()
-                    tickets.append((ok.numpy().tolist(), hd, ep.d_agg_sig[(k - 1) & 1].cpu().numpy().copy()))
+                    collect(t)
         elif mode == "sync":
             ok, hd = ep.process_epoch_dev(*d)
             torch.cuda.synchronize()
@@ -111,12 +116,10 @@ def test_epoch_pipeline_matches_oracle(mode):
         else:
             t = ep.submit_dev(*d)
             if t is not None:
-                ok, hd = t.wait()
-                slot_prev = (k - 1) & 1
-                tickets.append((ok.cpu().numpy().tolist(), hd, ep.d_agg_sig[slot_prev].cpu().numpy().copy()))
+                collect(t)
     if mode in ("pipelined", "pipelined_host"):
-        ok, hd = ep.drain().wait()
-        tickets.append((ok.cpu().numpy().tolist(), hd, ep.d_agg_sig[(n_epochs - 1) & 1].cpu().numpy().copy()))
+        for t in ep.drain():
+            collect(t)
     assert len(tickets) == n_epochs
     for k in range(n_epochs):
         aggs, oks, head = expected[k]
