@@ -1,5 +1,5 @@
 # diagnostic sweep of the launch-shape knobs of libb200pos.so (B2_TAIL_BLOCK, B2_DEC_BLOCK, B2_PAIRING_FORM) and the pipeline depth; run on the B200
-for cfg in "128 128 auto 2" "128 128 auto 3" "128 128 auto 4" "32 128 auto 3" "128 128 team 3" "128 64 auto 3"; do
+for cfg in "128 128 auto 3" "32 128 auto 3" "64 128 auto 3" "128 128 auto 4" "128 128 auto 3"; do
   set -- $cfg
   B2_TAIL_BLOCK=$1 B2_DEC_BLOCK=$2 B2_PAIRING_FORM=$3 timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --depth $4 2>/dev/null | python -c "
 import sys, json
