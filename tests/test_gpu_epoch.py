@@ -49,6 +49,18 @@ def _epoch_inputs(k, members, off, rng):
     return msgs, bits, sigs, target_epoch, block_idx
 
 
+_CACHE = {}
+
+
+def _epoch_case(k, pks, members, off):
+    """Inputs and oracle results of epoch k; the same for every mode, so the (pure-Python, slow) oracle runs once per epoch."""
+    if k not in _CACHE:
+        msgs, bits, sigs, te, bi = _epoch_inputs(k, members, off, None)
+        aggs, oks = _expected(pks, members, off, msgs, bits, sigs)
+        _CACHE[k] = (msgs, bits, sigs, te, bi, aggs, oks)
+    return _CACHE[k]
+
+
 def _expected(pks, members, off, msgs, bits, sigs):
     aggs, oks = [], []
     for a in range(N_AGG):
@@ -85,8 +97,7 @@ def test_epoch_pipeline_matches_oracle(mode, depth):
     expected, tickets, keep_alive = [], [], []
     n_epochs = 6
     for k in range(n_epochs):
-        msgs, bits, sigs, te, bi = _epoch_inputs(k, members, off, rng)
-        aggs, oks = _expected(pks, members, off, msgs, bits, sigs)
+        msgs, bits, sigs, te, bi, aggs, oks = _epoch_case(k, pks, members, off)
         assert sum(oks) == N_AGG - 3 and oks[5] == 1 and oks[9] == 0
         for a in range(N_AGG):                      # sequential oracle for the LMD table
             if oks[a]:
