@@ -35,7 +35,7 @@ SLOTS, COMMITTEES_PER_SLOT, COMMITTEE_SIZE = 32, 64, 512
 N_AGG = SLOTS * COMMITTEES_PER_SLOT
 N_BLOCKS = 10000
 R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
-TRAFFIC_BYTES_K3 = 1.80e9      # dram read 0.15 GB + write 1.65 GB per launch (per-thread window tables in local memory), ncu r1 capture
+TRAFFIC_BYTES_K3 = 1.40e9      # dram read 0.17 GB + write 1.23 GB per k_g2_decompress launch (affine points + window-table evictions), ncu r1c capture
 WORKLOAD = "full epoch: 32 slots x 64 committees x 512 members = 2^20 validators per rank; 10000-block fork tree"
 
 
@@ -402,7 +402,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": "bls.Aggregate (k_g2_decompress + k_g2_segment_sum)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES_K3, "peak_source": peak_src,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_g2_decompress (profiles/)",
-                         "note": "integer-pipe bound, not HBM bound (ncu: sm__pipe_fmaheavy_cycles_active 95%, DRAM 0.6% of peak); see int_pipe and DESIGN.md",
+                         "note": "integer-pipe bound, not HBM bound (ncu: sm__pipe_fmaheavy_cycles_active 89%, DRAM 0.7% of peak); see int_pipe and DESIGN.md",
                          "int_pipe": {"achieved": int_ach / 1e12, "peak": int_peak / 1e12, "unit": "T wide-MAC/s", "frac": int_ach / int_peak,
                                       "wide_mac_per_signature": wide_per_sig}},
             "setup_s": W["setup_s"],

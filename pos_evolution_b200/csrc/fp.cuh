@@ -16,6 +16,10 @@
 #pragma once
 #include "consts.cuh"
 
+#ifndef B2_SQR_KARATSUBA
+#define B2_SQR_KARATSUBA 0
+#endif
+
 namespace b2 {
 
 struct fp {
@@ -175,47 +179,94 @@ HD void mont_shift_row(uint32_t* E, uint32_t* X) {            // mont_mul_row wi
     X[11] = 0u;
 }
 
-HD fp fp_sqr(const fp& a) {
-    uint32_t ue[24], uo[24];
+// 2N-limb square of an N-limb number (N even), separated operand scanning as described above: N(N-1)/2 + N wide products.
+template <int N>
+HD void sqr_limbs(const uint32_t* a, uint32_t* t) {
+    uint32_t ue[2 * N], uo[2 * N];
 #pragma unroll
-    for (int k = 0; k < 24; k++) ue[k] = uo[k] = 0u;
+    for (int k = 0; k < 2 * N; k++) ue[k] = uo[k] = 0u;
 #pragma unroll
-    for (int i = 0; i < 11; i++) {
+    for (int i = 0; i < N - 1; i++) {
         {   // j = i+1, i+3, ...  -> odd-aligned pairs
-            mad_wide_cc(uo[2 * i + 1], uo[2 * i + 2], a.l[i], a.l[i + 1]);
+            mad_wide_cc(uo[2 * i + 1], uo[2 * i + 2], a[i], a[i + 1]);
             int s = 2 * i + 1;
 #pragma unroll
-            for (int j = i + 3; j < 12; j += 2) {
+            for (int j = i + 3; j < N; j += 2) {
                 s = i + j;
-                madc_wide_cc(uo[s], uo[s + 1], a.l[i], a.l[j]);
+                madc_wide_cc(uo[s], uo[s + 1], a[i], a[j]);
             }
-            if (s + 2 < 24) uo[s + 2] = addc(uo[s + 2], 0u);
+            if (s + 2 < 2 * N) uo[s + 2] = addc(uo[s + 2], 0u);
         }
-        if (i + 2 < 12) {   // j = i+2, i+4, ...  -> even-aligned pairs
-            mad_wide_cc(ue[2 * i + 2], ue[2 * i + 3], a.l[i], a.l[i + 2]);
+        if (i + 2 < N) {   // j = i+2, i+4, ...  -> even-aligned pairs
+            mad_wide_cc(ue[2 * i + 2], ue[2 * i + 3], a[i], a[i + 2]);
             int s = 2 * i + 2;
 #pragma unroll
-            for (int j = i + 4; j < 12; j += 2) {
+            for (int j = i + 4; j < N; j += 2) {
                 s = i + j;
-                madc_wide_cc(ue[s], ue[s + 1], a.l[i], a.l[j]);
+                madc_wide_cc(ue[s], ue[s + 1], a[i], a[j]);
             }
-            if (s + 2 < 24) ue[s + 2] = addc(ue[s + 2], 0u);
+            if (s + 2 < 2 * N) ue[s + 2] = addc(ue[s + 2], 0u);
         }
     }
     // t = 2*(ue + uo) + sum a_i^2 B^(2i)
-    uint32_t t[24], d[24];
+    uint32_t d[2 * N];
     t[0] = add_cc(ue[0], uo[0]);
 #pragma unroll
-    for (int k = 1; k < 24; k++) t[k] = addc_cc(ue[k], uo[k]);
-    // doubling by funnel shifts (24 independent ops instead of a 24-long carry chain); the sum is < 2^767, nothing is shifted out
+    for (int k = 1; k < 2 * N; k++) t[k] = addc_cc(ue[k], uo[k]);
+    // doubling by funnel shifts (independent ops instead of a carry chain); the off-diagonal sum is < 2^(64N-1), nothing is shifted out
 #pragma unroll
-    for (int k = 23; k >= 1; k--) t[k] = (t[k] << 1) | (t[k - 1] >> 31);
+    for (int k = 2 * N - 1; k >= 1; k--) t[k] = (t[k] << 1) | (t[k - 1] >> 31);
     t[0] <<= 1;
 #pragma unroll
-    for (int i = 0; i < 12; i++) mul_wide(d[2 * i], d[2 * i + 1], a.l[i], a.l[i]);
+    for (int i = 0; i < N; i++) mul_wide(d[2 * i], d[2 * i + 1], a[i], a[i]);
     t[0] = add_cc(t[0], d[0]);
 #pragma unroll
-    for (int k = 1; k < 24; k++) t[k] = addc_cc(t[k], d[k]);
+    for (int k = 1; k < 2 * N - 1; k++) t[k] = addc_cc(t[k], d[k]);
+    t[2 * N - 1] = addc(t[2 * N - 1], d[2 * N - 1]);
+}
+
+// 24-limb square of a 12-limb number.  One Karatsuba level over 6-limb halves a = a0 + a1*2^192:
+//   a^2 = a0^2 + (a0^2 + a1^2 - (a0 - a1)^2) * 2^192 + a1^2 * 2^384
+// i.e. three 6-limb squares (63 wide products) instead of 78; the additions are IADD3 work on the ALU pipe.
+HD void sqr_product(const uint32_t* a, uint32_t* t) {
+#if B2_SQR_KARATSUBA
+    uint32_t dd[6], D[12], M[13];
+    // dd = |a0 - a1|
+    dd[0] = sub_cc(a[0], a[6]);
+#pragma unroll
+    for (int k = 1; k < 6; k++) dd[k] = subc_cc(a[k], a[6 + k]);
+    const uint32_t neg = subc(0u, 0u);                      // all-ones when a0 < a1
+    dd[0] = add_cc(dd[0] ^ neg, neg & 1u);
+#pragma unroll
+    for (int k = 1; k < 5; k++) dd[k] = addc_cc(dd[k] ^ neg, 0u);
+    dd[5] = addc(dd[5] ^ neg, 0u);
+    sqr_limbs<6>(a, t);                                     // L = a0^2 -> t[0..11]
+    sqr_limbs<6>(a + 6, t + 12);                            // H = a1^2 -> t[12..23]
+    sqr_limbs<6>(dd, D);
+    // M = L + H - D = 2 a0 a1  (< 2^385: 13 limbs)
+    M[0] = add_cc(t[0], t[12]);
+#pragma unroll
+    for (int k = 1; k < 12; k++) M[k] = addc_cc(t[k], t[12 + k]);
+    M[12] = addc(0u, 0u);
+    M[0] = sub_cc(M[0], D[0]);
+#pragma unroll
+    for (int k = 1; k < 12; k++) M[k] = subc_cc(M[k], D[k]);
+    M[12] = subc(M[12], 0u);
+    // t += M * 2^192
+    t[6] = add_cc(t[6], M[0]);
+#pragma unroll
+    for (int k = 1; k < 13; k++) t[6 + k] = addc_cc(t[6 + k], M[k]);
+#pragma unroll
+    for (int k = 19; k < 23; k++) t[k] = addc_cc(t[k], 0u);
+    t[23] = addc(t[23], 0u);
+#else
+    sqr_limbs<12>(a, t);
+#endif
+}
+
+HD fp fp_sqr(const fp& a) {
+    uint32_t t[24];
+    sqr_product(a.l, t);
     // Montgomery-reduce the low half (result <= p), add the high half (< p/8): the sum is < 2p
     uint32_t ev[12], od[12];
 #pragma unroll

@@ -232,7 +232,10 @@ def test_fp_sqr_dedicated():
     for a in edge + [rfp() for _ in range(5000)]:
         assert hs.fp_v(call(lib.hs_fp_sqr, hs.fp_m(a), out_words=12)) == a * a % P
     # raw limb patterns (the Montgomery image is what the chains see): all-ones limbs below p, alternating, sparse
-    for raw in (P - 1, P - 2, int("ffffffff" * 11, 16), int("ffffffff00000000" * 5 + "ffffffff", 16), 1 << 352, (1 << 352) - 1):
+    half = (1 << 192) - 1
+    for raw in (P - 1, P - 2, int("ffffffff" * 11, 16), int("ffffffff00000000" * 5 + "ffffffff", 16), 1 << 352, (1 << 352) - 1,
+                # the 6-limb halves a0, a1 of the Karatsuba split: equal, zero, all-ones, a0 < a1, a0 > a1 by one
+                half, half << 192, (0x1234 << 192) | 0x1234, (7 << 192) | 6, (6 << 192) | 7, ((half >> 8) << 192) | half, (1 << 192) | half, 1 << 192, 1):
         raw %= P
         arr = np.array(hs.limbs(raw), dtype=np.uint32)
         got = call(lib.hs_fp_sqr, arr, out_words=12)

@@ -2,7 +2,7 @@
 // Every thread computes a^((p-3)/4) for its own a; a warp takes its work in chunks of 32 from a global counter, so faster
 // warps take more.  mode 0: all warps integer form (fp.cuh), 1: all warps FP64 form (fpd.cuh), 2: blocks alternate per SM.
 // Also checks that both forms give identical limbs.
-// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I pos_evolution_b200/csrc -I tools/experiments -o /tmp/pmix tools/pow_mix_bench.cu
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I pos_evolution_b200/csrc -I tools/experiments -o /tmp/pmix tools/pow_mix_bench.cu   (add -DB2_SQR_KARATSUBA=1 to time the Karatsuba squaring)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
