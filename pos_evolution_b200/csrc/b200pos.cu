@@ -48,6 +48,11 @@ struct b2_ctx {
     // threads per block of k_g2_decompress: its blocks fill the register file, so a smaller block is what a pairing warp of the
     // previous epoch displaces when the two overlap
     unsigned dec_block = 128;
+    // SMs the persistent decompression kernel of the pipelined epoch path leaves empty for the pairing tails (kernels.cuh).
+    // 0 = off (the default: measured slower); B2_RESERVE_SMS=n turns the experiment on.
+    unsigned reserve_sms = 0;
+    sm_mask reserved = {{0, 0, 0, 0}};
+    unsigned long long* d_dec_counter = nullptr;      // one work counter per epoch slot
     unsigned long long fc_min_key = 0;
     int fc_exclude_slashed = 0;
     // epoch participation flags (0 = current, 1 = previous) and the per-(validator, flag) election table
@@ -146,6 +151,37 @@ int b2_init(int device, b2_ctx** out) {
         if (v == 32 || v == 64 || v == 128) ctx->tail_block = v;
     }
     if (const char* e = getenv("B2_PAIRING_FORM")) ctx->pairing_form = !strcmp(e, "team") ? 1 : (!strcmp(e, "thread") ? 2 : 0);
+    if (const char* e = getenv("B2_RESERVE_SMS")) {
+        unsigned v = (unsigned)atoi(e);
+        if (v < (unsigned)ctx->n_sm / 2) ctx->reserve_sms = v;
+    }
+    if (ctx->reserve_sms >= (unsigned)ctx->n_sm / 2) ctx->reserve_sms = ctx->n_sm / 9;
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_dec_counter, sizeof(unsigned long long) * B2_EPOCH_SLOTS);
+    if (e == cudaSuccess && ctx->reserve_sms > 0) {
+        // the SM ids that exist (they need not be 0..n_sm-1); reserve the highest `reserve_sms` of them
+        unsigned int* d_seen = nullptr;
+        unsigned int seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        e = cudaMalloc(&d_seen, sizeof(seen));
+        if (e == cudaSuccess) e = cudaMemset(d_seen, 0, sizeof(seen));
+        if (e == cudaSuccess) {
+            k_probe_smid<<<ctx->n_sm * 8, 64>>>(d_seen);
+            e = cudaMemcpy(seen, d_seen, sizeof(seen), cudaMemcpyDeviceToHost);
+        }
+        if (d_seen) cudaFree(d_seen);
+        unsigned left = ctx->reserve_sms, found = 0;
+        for (int id = 255; id >= 0; id--) {
+            if (!((seen[id >> 5] >> (id & 31)) & 1u)) continue;
+            found++;
+            if (left) {
+                ctx->reserved.w[id >> 6] |= 1ull << (id & 63);
+                left--;
+            }
+        }
+        if (found < (unsigned)ctx->n_sm) {          // the probe did not reach every SM: do not reserve blindly
+            ctx->reserved = sm_mask{{0, 0, 0, 0}};
+            ctx->reserve_sms = 0;
+        }
+    }
     if (const char* e = getenv("B2_DEC_BLOCK")) {
         unsigned v = (unsigned)atoi(e);
         if (v == 32 || v == 64 || v == 128) ctx->dec_block = v;
@@ -186,6 +222,7 @@ void b2_destroy(b2_ctx* ctx) {
         if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->ev_lmd_done) cudaEventDestroy(ctx->ev_lmd_done);
+    if (ctx->d_dec_counter) cudaFree(ctx->d_dec_counter);
     if (ctx->ev_votes_done) cudaEventDestroy(ctx->ev_votes_done);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
@@ -307,12 +344,17 @@ int b2_g1_aggregate(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, c
 // front: stage 1 + 2 (decompress every signature, per-segment Jacobian sums into V.sumjac);  finish: stage 3 (one
 // inversion per segment -> compressed bytes; with `handoff` also the affine point + subgroup-checked flag for verify_main).
 static int aggregate_front(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig,
-                           int32_t* d_seg_status, cudaStream_t s) {
+                           int32_t* d_seg_status, cudaStream_t s, int reserve_slot = -1) {
     int rc;
     if ((rc = ensure(ctx, ctx->sc_g2aff, (size_t)n_sig * 192 + 16)) || (rc = ensure(ctx, ctx->sc_g2st, n_sig + 16)) ||
         (rc = ensure(ctx, V.sumjac, (size_t)n_seg * 288)))
         return rc;
-    if (n_sig) {
+    if (n_sig && reserve_slot >= 0 && ctx->reserve_sms > 0 && n_sig >= (uint64_t)ctx->n_sm * 512) {
+        unsigned long long* ctr = ctx->d_dec_counter + reserve_slot;
+        CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
+        k_g2_decompress_persistent<<<ctx->n_sm * 4, 128, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p, ctr, ctx->reserved);
+        CKL(ctx);
+    } else if (n_sig) {
         k_g2_decompress<<<blocks_for(n_sig, ctx->dec_block), ctx->dec_block, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p);
         CKL(ctx);
     }
@@ -481,7 +523,7 @@ static int epoch_start(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint
     CK(cudaStreamWaitEvent(s, V.ev_tail_done, 0));      // the slot's previous user (B2_EPOCH_SLOTS-or-fewer epochs ago) must have drained
     pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
     if ((rc = verify_fork(ctx, V, P, d_msg32, n_agg, s, team))) return rc;
-    if ((rc = aggregate_front(ctx, V, d_sig96, d_off, n_agg, n_sig, d_agg_status, s))) return rc;
+    if ((rc = aggregate_front(ctx, V, d_sig96, d_off, n_agg, n_sig, d_agg_status, s, team ? -1 : slot))) return rc;
     CK(cudaEventRecord(V.ev_seg, s));
     return B2_OK;
 }

@@ -225,9 +225,12 @@ HD void sqr_limbs(const uint32_t* a, uint32_t* t) {
     t[2 * N - 1] = addc(t[2 * N - 1], d[2 * N - 1]);
 }
 
-// 24-limb square of a 12-limb number.  One Karatsuba level over 6-limb halves a = a0 + a1*2^192:
+// 24-limb square of a 12-limb number.  B2_SQR_KARATSUBA selects one Karatsuba level over 6-limb halves a = a0 + a1*2^192:
 //   a^2 = a0^2 + (a0^2 + a1^2 - (a0 - a1)^2) * 2^192 + a1^2 * 2^384
-// i.e. three 6-limb squares (63 wide products) instead of 78; the additions are IADD3 work on the ALU pipe.
+// i.e. three 6-limb squares (63 wide products) instead of 78.  MEASURED SLOWER on the B200 and therefore off: 2^20 exponentiations
+// take 15.5 ms instead of 14.4 ms (tools/pow_mix_bench.cu, profiles/r1c_karatsuba_ab.txt).  ptxas turns part of the extra carry
+// bookkeeping into IMAD.X / IMAD.MOV (190 + 94 instead of 209 + 47 instructions on the FMA pipes per squaring), which costs more
+// multiply-pipe time than the 19 wide products save.  Kept, tested by tests/test_hostsim.py, as the record of that experiment.
 HD void sqr_product(const uint32_t* a, uint32_t* t) {
 #if B2_SQR_KARATSUBA
     uint32_t dd[6], D[12], M[13];

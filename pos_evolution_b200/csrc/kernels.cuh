@@ -118,6 +118,50 @@ __global__ void __launch_bounds__(128, 4) k_g2_decompress(const uint8_t* __restr
     for (int k = 0; k < 12; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
     st_out[i] = (uint8_t)st;
 }
+// stage 1, pipelined form.  Same work, but as a PERSISTENT grid (4 blocks per SM -- these blocks fill the register file, so nothing
+// else fits beside them) whose warps take 32 signatures at a time from a global counter, and whose blocks EXIT at once when they
+// find themselves on one of the SMs named in `reserved` (bit i of word i/64 <-> %smid i).  The reserved SMs stay empty for the
+// pairing tail of the previous epochs (whose blocks fit nowhere else while this grid is resident): a tail warp that has a scheduler
+// to itself runs the multiply pipe at ~90 %, one that shares it with four decompression warps crawls and, worse, evicts them
+// (profiles/README.md).  Which SM ends up doing how much is decided by the counter, not by the launch geometry.
+struct sm_mask {
+    unsigned long long w[4];
+};
+__global__ void __launch_bounds__(128, 4) k_g2_decompress_persistent(const uint8_t* __restrict__ sig96, uint64_t n, uint32_t* aff_out, uint8_t* st_out,
+                                                                      unsigned long long* counter, sm_mask reserved) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid < 256 && ((reserved.w[smid >> 6] >> (smid & 63)) & 1ull)) return;
+    const uint32_t lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint64_t i = base + lane;
+        if (i < n) {
+            g2_aff s;
+            s.x = fp2_zero();
+            s.y = fp2_zero();
+            int st = g2_decompress(sig96 + 96 * i, s);
+            uint4* o = reinterpret_cast<uint4*>(aff_out + 48 * i);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&s);
+#pragma unroll
+            for (int k = 0; k < 12; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            st_out[i] = (uint8_t)st;
+        }
+    }
+}
+// which SM ids exist on this device (b2_init: the reserved set is chosen among the ids actually seen)
+__global__ void k_probe_smid(unsigned int* seen) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (threadIdx.x == 0 && smid < 256) atomicOr(&seen[smid >> 5], 1u << (smid & 31));
+    // stay resident for a moment so that the grid spreads over every SM
+    const long long t0 = clock64();
+    while (clock64() - t0 < 20000) {
+    }
+}
 // stage 2: one WARP per segment (each lane adds every 32nd point, then a 5-round shuffle tree) -> Jacobian sum (72 words) + status.  The inversion needed for
 // the compressed encoding is NOT done here (127 threads would idle behind it): stage 3 does it with a thread per segment.
 __global__ void __launch_bounds__(32) k_g2_segment_sum(const uint32_t* __restrict__ aff, const uint8_t* __restrict__ st,
