@@ -248,9 +248,9 @@ def run_gpu(args):
     def run_pipelined_dev(n):
         """n epochs through the software pipeline; every epoch's result is complete (for the current stream) when this returns."""
         results = []
-        for _ in range(n):
+        for i in range(n):
             d_epoch.add_(1)
-            t = ep.submit_dev(d_sigs, d_bits, d_msgs, d_epoch, d_blk, 0, boost_idx, boost)
+            t = ep.submit_dev(d_sigs, d_bits, d_msgs, d_epoch, d_blk, 0, boost_idx, boost, last=(i == n - 1))
             if t is not None:
                 results.append(t)
         results.extend(ep.drain())
@@ -258,11 +258,11 @@ def run_gpu(args):
 
     def run_pipelined_host(n):
         results = []
-        for _ in range(n):
+        for i in range(n):
             host_epoch_counter[0] += 1
             he = h_epochs[host_epoch_counter[0] % len(h_epochs)]   # a pinned buffer is rewritten only after the epoch that read it has completed
             he.fill_(1000 + host_epoch_counter[0])
-            t = ep.submit_host(h_sigs, h_bits, h_msgs, he, h_blk, 0, boost_idx, boost)
+            t = ep.submit_host(h_sigs, h_bits, h_msgs, he, h_blk, 0, boost_idx, boost, last=(i == n - 1))
             if t is not None:
                 results.append(t.wait())               # host blocks on the D2H of the epoch submitted depth-1 calls ago
         for t in ep.drain():
@@ -436,7 +436,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

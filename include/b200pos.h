@@ -172,6 +172,10 @@ int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const ui
                       const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
                       uint8_t* d_ok_out);
 int b2_epoch_wait_dev(b2_ctx* ctx, int slot, void* stream);
+/* Which form of the pairing kernels (K5/K6) b2_epoch_start_dev / b2_epoch_tail_dev enqueue from now on: 0 = thread per aggregate
+ * (fewest instructions: right while further epochs keep the chip busy), 1 = three lanes per pairing (shortest critical path: right for
+ * the last epochs of a batch, whose tails drain with nothing left to overlap).  The synchronous entry points always use form 1. */
+int b2_epoch_set_pairing_form(b2_ctx* ctx, int form);
 int b2_latest_messages_update_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                                   uint32_t bits_stride, const uint64_t* d_target_epoch, const uint32_t* d_block_idx,
                                   const uint8_t* d_accept, uint32_t n_agg, void* stream);

@@ -44,6 +44,7 @@ struct b2_ctx {
     // fork-choice variants: votes older than fc_min_key (epoch << 32) expire; v1.3 get_weight skips slashed validators
     // threads per block of the thread-per-aggregate kernels when they run under the epoch pipeline (see launch_miller)
     unsigned tail_block = 128;
+    bool epoch_team = false;   // b2_epoch_set_pairing_form
     int pairing_form = 0;      // 0: team kernels for the synchronous calls, thread-per-aggregate under the pipeline; 1: always team; 2: always thread
     // threads per block of k_g2_decompress: its blocks fill the register file, so a smaller block is what a pairing warp of the
     // previous epoch displaces when the two overlap
@@ -565,7 +566,8 @@ int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint
             "epoch_start_dev: bad arguments");
     REQUIRE(ctx->n_val > 0, "epoch_start_dev: registry not loaded");
     CK(cudaSetDevice(ctx->device));
-    return epoch_start(ctx, slot, d_sig96, d_members, d_off, d_bits, bits_stride, d_msg32, n_agg, n_sig, d_agg_status, (cudaStream_t)stream, false);
+    return epoch_start(ctx, slot, d_sig96, d_members, d_off, d_bits, bits_stride, d_msg32, n_agg, n_sig, d_agg_status, (cudaStream_t)stream,
+                       ctx->epoch_team);
 }
 int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
                       const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
@@ -574,7 +576,12 @@ int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const ui
                 n_agg > 0 && bits_stride > 0, "epoch_tail_dev: bad arguments");
     CK(cudaSetDevice(ctx->device));
     return epoch_tail(ctx, slot, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, n_agg, d_agg_sig96, d_agg_status, d_ok_out,
-                      ctx->slot[slot].s_tail, false);
+                      ctx->slot[slot].s_tail, ctx->epoch_team);
+}
+int b2_epoch_set_pairing_form(b2_ctx* ctx, int form) {
+    REQUIRE(ctx && (form == 0 || form == 1), "epoch_set_pairing_form: bad arguments");
+    ctx->epoch_team = form == 1;
+    return B2_OK;
 }
 int b2_epoch_wait_dev(b2_ctx* ctx, int slot, void* stream) {
     REQUIRE(ctx && slot >= 0 && slot < B2_EPOCH_SLOTS, "epoch_wait_dev: bad arguments");

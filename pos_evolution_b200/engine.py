@@ -285,6 +285,9 @@ class Engine:
                                             d_target_epoch.data_ptr(), d_block_idx.data_ptr(), n_agg, d_agg_sig.data_ptr(), d_agg_status.data_ptr(),
                                             d_ok.data_ptr()))
 
+    def epoch_set_pairing_form(self, team: bool):
+        self._ck(self.lib.b2_epoch_set_pairing_form(self.h, 1 if team else 0))
+
     def epoch_wait_dev(self, slot):
         self._ck(self.lib.b2_epoch_wait_dev(self.h, int(slot), self._stream()))
 

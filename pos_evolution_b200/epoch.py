@@ -70,6 +70,7 @@ class EpochProcessor:
         self.ev_fc = [None] * S       # per slot: fork choice (+ D2H) of the epoch that last used the slot
         self.k = 0
         self._inflight = collections.deque()      # tickets of the submitted, not yet returned epochs
+        self._team_form = False
 
     def set_committees(self, members, off):
         """members u32[n_sig] (committee order), off u32[n_agg+1]; signature j belongs to member j."""
@@ -110,8 +111,11 @@ class EpochProcessor:
         return self.h_ok[s], int(self.h_head[s][0])
 
     # ------------------------------------------------------------------ pipelined form
-    def _submit(self, slot, d_sigs, d_bits, d_msgs, fc, host):
+    def _submit(self, slot, d_sigs, d_bits, d_msgs, fc, host, last=False):
         e = self.eng
+        if last != self._team_form:                       # last epoch of a batch: nothing will overlap its tail, so take the short form
+            e.epoch_set_pairing_form(last)
+            self._team_form = last
         e.epoch_start_dev(slot, d_sigs, self.d_members, self.d_off, d_bits, d_msgs, self.d_agg_status[slot])
         e.epoch_tail_dev(slot, self.d_members, self.d_off, d_bits, self.s_epoch[slot], self.s_blk[slot], self.d_agg_sig[slot],
                          self.d_agg_status[slot], self.d_ok[slot])
@@ -138,15 +142,16 @@ class EpochProcessor:
             stream.wait_event(self.ev_fc[slot])
         return slot
 
-    def submit_dev(self, d_sigs, d_bits, d_msgs, d_target_epoch, d_block_idx, justified_idx=0, boost_idx=-1, boost_score=0):
+    def submit_dev(self, d_sigs, d_bits, d_msgs, d_target_epoch, d_block_idx, justified_idx=0, boost_idx=-1, boost_score=0, last=False):
         """Enqueue one epoch (device-resident inputs, which must stay untouched until its ticket has been waited for).
-        Returns the ticket of the epoch submitted depth-1 calls earlier (None while the pipeline fills)."""
+        Returns the ticket of the epoch submitted depth-1 calls earlier (None while the pipeline fills).
+        `last=True` says no further epoch follows soon: its pairing tail is enqueued in the short-critical-path (team) form."""
         slot = self._claim_slot(torch.cuda.current_stream())
         self.s_epoch[slot].copy_(d_target_epoch)
         self.s_blk[slot].copy_(d_block_idx)
-        return self._submit(slot, d_sigs, d_bits, d_msgs, (justified_idx, boost_idx, boost_score), False)
+        return self._submit(slot, d_sigs, d_bits, d_msgs, (justified_idx, boost_idx, boost_score), False, last)
 
-    def submit_host(self, h_sigs, h_bits, h_msgs, h_target_epoch, h_block_idx, justified_idx=0, boost_idx=-1, boost_score=0):
+    def submit_host(self, h_sigs, h_bits, h_msgs, h_target_epoch, h_block_idx, justified_idx=0, boost_idx=-1, boost_score=0, last=False):
         """Pinned host tensors in (untouched until the returned-later ticket has been waited for).  The H2D copies go on a
         separate stream so that they overlap with the epochs in flight."""
         cur = torch.cuda.current_stream()
@@ -160,7 +165,7 @@ class EpochProcessor:
             ev = torch.cuda.Event()
             ev.record()
         cur.wait_event(ev)
-        return self._submit(slot, self.s_sigs[slot], self.s_bits[slot], self.s_msgs[slot], (justified_idx, boost_idx, boost_score), True)
+        return self._submit(slot, self.s_sigs[slot], self.s_bits[slot], self.s_msgs[slot], (justified_idx, boost_idx, boost_score), True, last)
 
     def drain(self):
         """Tickets of the epochs still in flight, oldest first; the current stream waits for all of them."""
