@@ -1063,12 +1063,3 @@ int b2_get_head(b2_ctx* ctx, uint32_t justified_idx, int32_t boost_idx, uint64_t
 }
 
 }  // extern "C"
-
-// debug helper (not part of the public header): read back the shuffle's per-round source table and pivots
-extern "C" int b2_debug_shuffle_tables(b2_ctx* ctx, uint8_t* src_out, size_t src_bytes, uint64_t* pivots_out, uint32_t rounds) {
-    if (!ctx || !ctx->sc_shuf.p || !ctx->sc_pivot.p) return B2_EINVAL;
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpy(src_out, ctx->sc_shuf.p, src_bytes, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(pivots_out, ctx->sc_pivot.p, (size_t)rounds * 8, cudaMemcpyDeviceToHost));
-    return B2_OK;
-}
