@@ -1,4 +1,4 @@
-"""GPU parity of the fused epoch pipeline (b2_epoch_dev) and of its two-slot software-pipelined form against the oracle:
+"""GPU parity of the fused epoch pipeline (b2_epoch_dev) and of its software-pipelined form (depth 2, 3, 4) against the oracle:
 per-committee aggregate signatures (bytes), verdicts, the latest-message table and the head after every epoch."""
 import hashlib
 
@@ -117,7 +117,7 @@ def test_epoch_pipeline_matches_oracle(mode, depth):
                 ok, hd = ep.process_epoch_host(*h)
                 tickets.append((ok.numpy().tolist(), hd, ep.d_agg_sig[0].cpu().numpy().copy()))
             else:
-                t = ep.submit_host(*h)
+                t = ep.submit_host(*h, last=(k == n_epochs - 1))
                 if t is not None:
                     collect(t)
         elif mode == "sync":
@@ -125,7 +125,7 @@ def test_epoch_pipeline_matches_oracle(mode, depth):
             torch.cuda.synchronize()
             tickets.append((ok.cpu().numpy().tolist(), int(hd.item()), ep.d_agg_sig[0].cpu().numpy().copy()))
         else:
-            t = ep.submit_dev(*d)
+            t = ep.submit_dev(*d, last=(k % 3 == 2))          # exercises both pairing forms under the pipeline
             if t is not None:
                 collect(t)
     if mode in ("pipelined", "pipelined_host"):

@@ -25,21 +25,6 @@ def full():
     eng.close()
 
 
-def _oracle_after_epoch(W, bench, accepted, target_epoch, blk):
-    """numpy restatement of update_latest_messages for whole committees + get_weight/get_head (oracle/fast.py)."""
-    from oracle import fast
-    msg_block, has_msg, equiv, eff, active = [x.copy() for x in W["votes"]]
-    m_epoch = np.ones(bench.N_VAL, dtype=np.uint64)
-    members, off = W["members"], W["off"]
-    for a in np.nonzero(accepted)[0]:
-        sel = members[off[a]:off[a + 1]]
-        fast.lmd_update(m_epoch, msg_block, has_msg, equiv, sel, int(target_epoch[a]), int(blk[a]))
-    parent, roots, leaf_viable = W["tree"]
-    w = fast.ghost_weights(parent, msg_block, has_msg, eff, active, equiv, bench.N_BLOCKS - 1, W["boost"])
-    head = fast.ghost_head(parent, roots, fast.ghost_viable(parent, leaf_viable), w, 0)
-    return w, head, (m_epoch, msg_block, has_msg)
-
-
 def test_full_epoch_properties(full):
     eng, W, bench = full
     from pos_evolution_b200.epoch import EpochProcessor
@@ -114,7 +99,7 @@ def test_full_epoch_properties(full):
         want.append(fast.ghost_head(parent, roots, fast.ghost_viable(parent, leaf_viable), w, 0))
         dk = [torch.as_tensor(te, device=dev), torch.as_tensor(bk, device=dev)]
         keep.append(dk)
-        t = ep.submit_dev(d_sigs, bits1, d[2], dk[0], dk[1], 0, bench.N_BLOCKS - 1, W["boost"])
+        t = ep.submit_dev(d_sigs, bits1, d[2], dk[0], dk[1], 0, bench.N_BLOCKS - 1, W["boost"], last=(k == 3))   # last: team-form tail
         if t is not None:
             tickets.append(t.wait())
     tickets += [t.wait() for t in ep.drain()]
