@@ -126,6 +126,15 @@ int b2_participation_update(b2_ctx* ctx, int which, const uint32_t* members, con
                             const uint8_t* flag_mask, const uint8_t* accept, uint32_t n_agg, uint64_t effective_balance_increment,
                             uint64_t base_reward_per_increment, uint64_t* numerator_out);
 
+/* ---- FFG balance sums: the inputs of weigh_justification_and_finalization (pos-evolution.md:793-803, :817-837).
+ * out4[0] = get_total_active_balance (sum of effective balances, registry flag bit0 = active in the current epoch),
+ * out4[1] / out4[2] = get_total_balance(get_unslashed_participating_indices(state, flag_index, current / previous epoch)): validators
+ *           that are active in that epoch (flag bit0 / bit2), not slashed (bit1) and carry `flag_index` in the participation table
+ *           `which` = 0 / 1 (b2_participation_load; a table that was never loaded counts as all-zero),
+ * out4[3] = total active AND unslashed balance (the essay's prose reading of get_total_active_balance, :809).
+ * Raw sums: the caller applies max(EFFECTIVE_BALANCE_INCREMENT, .) as get_total_balance does. */
+int b2_ffg_balances(b2_ctx* ctx, uint32_t flag_index, uint64_t* out4);
+
 /* ---- fork-choice variants (pos-evolution.md:1411-1413, :1447-1461, :1549-1596):
  * b2_set_fork_choice_params: votes whose epoch is < min_vote_epoch do not count (vote expiry of the Goldfish / RLMD-GHOST family;
  *   0 = plain LMD-GHOST); exclude_slashed != 0 selects the v1.3 get_weight rule (slashed validators, registry flag bit1, do not count).

@@ -24,6 +24,7 @@ PARTICIPATION_FLAG_WEIGHTS = [14, 26, 14]
 PROPOSER_WEIGHT = 8
 WEIGHT_DENOMINATOR = 64
 BASE_REWARD_FACTOR = 64
+JUSTIFICATION_BITS_LENGTH = 4
 
 
 @dataclass(frozen=True)
@@ -120,6 +121,7 @@ class BeaconState:                     # ref :338-374 (only the fields the path 
     previous_justified_checkpoint: Checkpoint = Checkpoint()
     current_justified_checkpoint: Checkpoint = Checkpoint()
     finalized_checkpoint: Checkpoint = Checkpoint()
+    justification_bits: List[int] = field(default_factory=lambda: [0] * JUSTIFICATION_BITS_LENGTH)
 
 
 @dataclass
@@ -189,6 +191,44 @@ class Spec:
         tot = sum(state.validators[i].effective_balance
                   for i in self.get_active_validator_indices(state, self.get_current_epoch(state)))
         return max(self.p.EFFECTIVE_BALANCE_INCREMENT, tot)
+
+    def get_total_balance(self, state, indices):                             # ext; described at ref :811
+        return max(self.p.EFFECTIVE_BALANCE_INCREMENT, sum(state.validators[i].effective_balance for i in indices))
+
+    def get_unslashed_participating_indices(self, state, flag_index, epoch):   # ext; described at ref :805-807
+        cur = self.get_current_epoch(state)
+        assert epoch in (self.get_previous_epoch(state), cur)
+        table = state.current_epoch_participation if epoch == cur else state.previous_epoch_participation
+        return set(i for i in self.get_active_validator_indices(state, epoch)
+                   if self.has_flag(table[i], flag_index) and not state.validators[i].slashed)
+
+    # ------------------------------------------------------------------ FFG accounting (ref :793-803, :817-852)
+    def process_justification_and_finalization(self, state):
+        cur = self.get_current_epoch(state)
+        if cur <= GENESIS_EPOCH + 1:
+            return
+        prev_idx = self.get_unslashed_participating_indices(state, TIMELY_TARGET_FLAG_INDEX, self.get_previous_epoch(state))
+        cur_idx = self.get_unslashed_participating_indices(state, TIMELY_TARGET_FLAG_INDEX, cur)
+        self.weigh_justification_and_finalization(state, self.get_total_active_balance(state),
+                                                  self.get_total_balance(state, prev_idx), self.get_total_balance(state, cur_idx))
+
+    def weigh_justification_and_finalization(self, state, total_active_balance, previous_epoch_target_balance,
+                                             current_epoch_target_balance):
+        prev_epoch, cur_epoch = self.get_previous_epoch(state), self.get_current_epoch(state)
+        old_prev, old_cur = state.previous_justified_checkpoint, state.current_justified_checkpoint
+        state.previous_justified_checkpoint = old_cur
+        bits = [0] + [int(b) for b in state.justification_bits[:JUSTIFICATION_BITS_LENGTH - 1]]   # a new epoch enters at position 0
+        # justification: 2/3 of the active stake voted for the target (ref :830, :834); the current epoch overrides the previous one
+        for pos, epoch, balance in ((1, prev_epoch, previous_epoch_target_balance), (0, cur_epoch, current_epoch_target_balance)):
+            if 3 * balance >= 2 * total_active_balance:
+                state.current_justified_checkpoint = Checkpoint(epoch=epoch, root=self.get_block_root(state, epoch))
+                bits[pos] = 1
+        state.justification_bits = bits
+        # finalization, the four rules of ref :842-852 in their order:
+        # (bits [lo, hi) all justified, source checkpoint, distance of the source from the current epoch)
+        for lo, hi, source, dist in ((1, 4, old_prev, 3), (1, 3, old_prev, 2), (0, 3, old_cur, 2), (0, 2, old_cur, 1)):
+            if all(bits[lo:hi]) and source.epoch + dist == cur_epoch:
+                state.finalized_checkpoint = source
 
     def get_randao_mix(self, state, epoch):
         return state.randao_mixes[epoch % self.p.EPOCHS_PER_HISTORICAL_VECTOR]

@@ -900,6 +900,23 @@ int b2_participation_update(b2_ctx* ctx, int which, const uint32_t* members, con
     return B2_OK;
 }
 
+// ------------------------------------------------------------------------------------------ FFG balance sums (:793-803)
+int b2_ffg_balances(b2_ctx* ctx, uint32_t flag_index, uint64_t* out4) {
+    REQUIRE(ctx && out4 && flag_index < 8, "ffg_balances: bad arguments");
+    REQUIRE(ctx->n_val > 0, "ffg_balances: registry not loaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->out_b, 32))) return rc;
+    CK(cudaMemsetAsync(ctx->out_b.p, 0, 32, s));
+    k_ffg_balances<<<ctx->n_sm * 4, 256, 0, s>>>(ctx->n_val, (const unsigned long long*)ctx->d_eff, ctx->d_flags, (const uint8_t*)ctx->d_part[0],
+                                                 (const uint8_t*)ctx->d_part[1], flag_index, (unsigned long long*)ctx->out_b.p);
+    CKL(ctx);
+    CK(cudaMemcpyAsync(out4, ctx->out_b.p, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------------------------------ fork-choice variants
 int b2_set_fork_choice_params(b2_ctx* ctx, uint64_t min_vote_epoch, int exclude_slashed) {
     REQUIRE(ctx && min_vote_epoch < 0xffffffffull, "set_fork_choice_params: bad arguments");

@@ -868,6 +868,38 @@ __global__ void __launch_bounds__(128) k_part_phase3(const uint32_t* __restrict_
 }
 }  // namespace b2
 
+// ------------------------------------------------------------------------------------------ FFG balance sums
+// The three u64 sums process_justification_and_finalization feeds to weigh_justification_and_finalization
+// (/root/reference/pos-evolution.md:793-803): total active balance, and the balance of the unslashed validators that carry
+// `flag` in the current / previous epoch participation table (get_unslashed_participating_indices + get_total_balance).
+// Registry flag byte: bit0 active in the current epoch, bit1 slashed, bit2 active in the previous epoch.  22 B per validator,
+// one grid-stride pass, warp-shuffle + one atomicAdd per warp.  out[0] total active, out[1] current, out[2] previous,
+// out[3] total active AND unslashed (the essay's prose reading of get_total_active_balance, :809).
+namespace b2 {
+__global__ void __launch_bounds__(256) k_ffg_balances(uint64_t n, const unsigned long long* __restrict__ eff, const uint8_t* __restrict__ flags,
+                                                       const uint8_t* __restrict__ part_cur, const uint8_t* __restrict__ part_prev, uint32_t flag_bit,
+                                                       unsigned long long* out) {
+    unsigned long long s[4] = {0ull, 0ull, 0ull, 0ull};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t f = flags[i];
+        const unsigned long long e = eff[i];
+        const bool unslashed = !(f & 2u);
+        if (f & 1u) {
+            s[0] += e;
+            if (unslashed) s[3] += e;
+            if (unslashed && part_cur && ((part_cur[i] >> flag_bit) & 1u)) s[1] += e;
+        }
+        if ((f & 4u) && unslashed && part_prev && ((part_prev[i] >> flag_bit) & 1u)) s[2] += e;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) s[k] += __shfl_down_sync(0xffffffffu, s[k], d);
+        if ((threadIdx.x & 31) == 0 && s[k]) atomicAdd(&out[k], s[k]);
+    }
+}
+}  // namespace b2
+
 // ------------------------------------------------------------------------------------------ fork-choice variants
 // on_attester_slashing (/root/reference/pos-evolution.md:1447-1461): the validators in BOTH attesting-index lists become
 // equivocating (Store.equivocating_indices, :897) and stop counting in get_weight (:1411-1413).  One thread per element of the

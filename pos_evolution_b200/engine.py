@@ -217,6 +217,12 @@ class Engine:
                                                   int(increment), int(base_reward_per_increment), _p(num)))
         return num
 
+    def ffg_balances(self, flag_index: int):
+        """(total_active, current_epoch_flag_balance, previous_epoch_flag_balance, total_active_unslashed) -- pos-evolution.md:793-803."""
+        out = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.b2_ffg_balances(self.h, int(flag_index), _p(out)))
+        return tuple(int(x) for x in out)
+
     def set_fork_choice_params(self, min_vote_epoch: int = 0, exclude_slashed: bool = False):
         self._ck(self.lib.b2_set_fork_choice_params(self.h, int(min_vote_epoch), 1 if exclude_slashed else 0))
 

@@ -28,6 +28,7 @@ PARTICIPATION_FLAG_WEIGHTS = [14, 26, 14]
 PROPOSER_WEIGHT = 8
 WEIGHT_DENOMINATOR = 64
 BASE_REWARD_FACTOR = 64
+JUSTIFICATION_BITS_LENGTH = 4
 
 
 @dataclass(frozen=True)
@@ -129,6 +130,7 @@ class BeaconState:                     # :338-374 (fields the path reads/writes)
     previous_justified_checkpoint: Checkpoint = Checkpoint()
     current_justified_checkpoint: Checkpoint = Checkpoint()
     finalized_checkpoint: Checkpoint = Checkpoint()
+    justification_bits: List[int] = field(default_factory=lambda: [0] * JUSTIFICATION_BITS_LENGTH)
 
 
 @dataclass
@@ -257,6 +259,48 @@ class Spec:
         tot = sum(v.effective_balance for v in state.validators if v.activation_epoch <= e < v.exit_epoch)
         return max(self.p.EFFECTIVE_BALANCE_INCREMENT, tot)
 
+    def get_total_balance(self, state, indices):                             # described at :811
+        return max(self.p.EFFECTIVE_BALANCE_INCREMENT, sum(state.validators[i].effective_balance for i in indices))
+
+    def get_unslashed_participating_indices(self, state, flag_index, epoch):   # described at :805-807 (host set form)
+        cur = self.get_current_epoch(state)
+        assert epoch in (self.get_previous_epoch(state), cur)
+        table = state.current_epoch_participation if epoch == cur else state.previous_epoch_participation
+        return set(i for i in self.get_active_validator_indices(state, epoch)
+                   if self.has_flag(table[i], flag_index) and not state.validators[i].slashed)
+
+    # ------------------------------------------------------------------ FFG accounting (:793-803, :817-852)
+    def process_justification_and_finalization(self, state):
+        """:793-803.  The three balance sums (total active, previous / current epoch TIMELY_TARGET balance of unslashed
+        validators) are one pass over the device registry and participation tables (b2_ffg_balances); the 2/3 tests and the
+        four finalization rules are scalar host logic."""
+        cur = self.get_current_epoch(state)
+        if cur <= GENESIS_EPOCH + 1:
+            return
+        self.sync_registry(state)
+        eng = self.engine
+        eng.participation_load(0, np.asarray(state.current_epoch_participation, dtype=np.uint8))
+        eng.participation_load(1, np.asarray(state.previous_epoch_participation, dtype=np.uint8))
+        total, cur_target, prev_target, _ = eng.ffg_balances(TIMELY_TARGET_FLAG_INDEX)
+        inc = self.p.EFFECTIVE_BALANCE_INCREMENT                                # get_total_balance's floor
+        self.weigh_justification_and_finalization(state, max(inc, total), max(inc, prev_target), max(inc, cur_target))
+
+    def weigh_justification_and_finalization(self, state, total_active_balance, previous_epoch_target_balance,
+                                             current_epoch_target_balance):    # :817-852
+        prev_epoch, cur_epoch = self.get_previous_epoch(state), self.get_current_epoch(state)
+        old_prev, old_cur = state.previous_justified_checkpoint, state.current_justified_checkpoint
+        state.previous_justified_checkpoint = old_cur
+        bits = [0] + [int(b) for b in state.justification_bits[:JUSTIFICATION_BITS_LENGTH - 1]]
+        for pos, epoch, balance in ((1, prev_epoch, previous_epoch_target_balance), (0, cur_epoch, current_epoch_target_balance)):
+            if 3 * balance >= 2 * total_active_balance:                        # :830, :834
+                state.current_justified_checkpoint = Checkpoint(epoch=epoch, root=self.get_block_root(state, epoch))
+                bits[pos] = 1
+        state.justification_bits = bits
+        # :842-852 -- (bits [lo, hi) all set, source checkpoint, its distance from the current epoch), in the reference's order
+        for lo, hi, source, dist in ((1, 4, old_prev, 3), (1, 3, old_prev, 2), (0, 3, old_cur, 2), (0, 2, old_cur, 1)):
+            if all(bits[lo:hi]) and source.epoch + dist == cur_epoch:
+                state.finalized_checkpoint = source
+
     def get_randao_mix(self, state, epoch):
         return state.randao_mixes[epoch % self.p.EPOCHS_PER_HISTORICAL_VECTOR]
 
@@ -355,7 +399,10 @@ class Spec:
         n = len(state.validators)
         epoch = self.get_current_epoch(state)
         eff = np.fromiter((v.effective_balance for v in state.validators), dtype=np.uint64, count=n)
+        prev = self.get_previous_epoch(state)
+        # bit0 active in the current epoch, bit1 slashed, bit2 active in the previous epoch (the FFG sums need both epochs)
         flags = np.fromiter(((1 if v.activation_epoch <= epoch < v.exit_epoch else 0) | (2 if v.slashed else 0)
+                             | (4 if v.activation_epoch <= prev < v.exit_epoch else 0)
                              for v in state.validators), dtype=np.uint8, count=n)
         if key != self._registry_key:
             pk = np.frombuffer(b"".join(bytes(v.pubkey) for v in state.validators), dtype=np.uint8).reshape(n, 48)

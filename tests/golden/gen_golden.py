@@ -76,6 +76,12 @@ def main():
         "head": ns["get_head"](store).hex(),
         "weights": {rb[b].hex(): spec.get_latest_attesting_balance(store, rb[b]) for b in range(0, len(rb), 9)},
     }
+    # FFG accounting (ref :793-852): the reference's text executed on 40 generated end-of-epoch states (scenarios.ffg_case(seed))
+    out["ffg"] = []
+    for seed in range(40):
+        st = scenarios.ffg_case(copy.deepcopy(state), seed)
+        ns["process_justification_and_finalization"](st)
+        out["ffg"].append(dict(scenarios.ffg_outcome(st), seed=seed))
     with open(os.path.join(HERE, "literal_spec.json"), "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)
     print("wrote literal_spec.json")

@@ -24,7 +24,8 @@ def uint_to_bytes(v):
 
 
 REF_FUNCS = ["get_committee_count_per_slot", "get_seed", "compute_committee", "compute_shuffled_index",
-             "compute_proposer_index", "process_attestation", "get_head", "update_latest_messages"]
+             "compute_proposer_index", "process_attestation", "get_head", "update_latest_messages",
+             "process_justification_and_finalization", "weigh_justification_and_finalization"]
 
 
 def namespace(spec: S.Spec):
@@ -46,6 +47,11 @@ def namespace(spec: S.Spec):
         get_base_reward=spec.get_base_reward, has_flag=spec.has_flag, add_flag=spec.add_flag,
         increase_balance=spec.increase_balance,
         get_filtered_block_tree=spec.get_filtered_block_tree,
+        # FFG accounting (ref :793-852): constants and the helpers described only in prose (:805-811)
+        GENESIS_EPOCH=S.GENESIS_EPOCH, TIMELY_TARGET_FLAG_INDEX=S.TIMELY_TARGET_FLAG_INDEX,
+        JUSTIFICATION_BITS_LENGTH=S.JUSTIFICATION_BITS_LENGTH, Checkpoint=S.Checkpoint, get_block_root=spec.get_block_root,
+        get_unslashed_participating_indices=spec.get_unslashed_participating_indices,
+        get_total_active_balance=spec.get_total_active_balance, get_total_balance=spec.get_total_balance,
         get_latest_attesting_balance=spec.get_latest_attesting_balance,
     )
     ref_blocks.exec_functions(REF_FUNCS, ns)

@@ -114,3 +114,42 @@ def votes(n_validators: int, n_blocks: int, seed: int = 4):
     active = (rng.random(n_validators) >= 0.01).astype(np.uint8)
     eff = np.where(rng.random(n_validators) < 0.9, 32, rng.integers(16, 33, size=n_validators)).astype(np.uint64) * np.uint64(10**9)
     return msg_block, has_msg, equiv, active, eff
+
+
+def ffg_case(state, seed: int, mod=S):
+    """Mutates `state` into a deterministic end-of-epoch situation for process_justification_and_finalization (ref :793-852):
+    random TIMELY_TARGET participation in both tables, a few slashed / exited / not-yet-active validators, prior checkpoints and
+    justification bits chosen so that over the seeds every justification branch and every finalization rule fires."""
+    rng = np.random.default_rng(1000 + seed)
+    n = len(state.validators)
+    cur = int(rng.integers(2, 8))
+    state.slot = cur * 8 + 7                                   # last slot of the epoch (minimal preset: 8 slots)
+    p_cur, p_prev = (float(rng.choice([0.2, 0.6, 0.66, 0.7, 0.95])) for _ in range(2))
+    state.current_epoch_participation = [int(rng.integers(0, 8)) & 5 | (2 if rng.random() < p_cur else 0) for _ in range(n)]
+    state.previous_epoch_participation = [int(rng.integers(0, 8)) & 5 | (2 if rng.random() < p_prev else 0) for _ in range(n)]
+    for v in state.validators:
+        r = rng.random()
+        v.slashed = r < 0.06
+        v.activation_epoch, v.exit_epoch = 0, 2**64 - 1
+        if 0.06 <= r < 0.10:
+            v.exit_epoch = cur                                 # active in the previous epoch only
+        elif 0.10 <= r < 0.13:
+            v.activation_epoch = cur                           # active in the current epoch only
+        elif 0.13 <= r < 0.15:
+            v.exit_epoch = max(0, cur - 1)                     # active in neither
+        v.effective_balance = int(rng.choice([32, 32, 32, 31, 24, 16])) * 10**9
+    pj = int(rng.integers(max(0, cur - 3), cur))               # previous_justified epoch in [cur-3, cur-1]
+    cj = int(rng.integers(max(pj, cur - 2), cur))              # current_justified epoch in [max(pj, cur-2), cur-1]
+    root = lambda e: _h(b"b200pos/cp" + int(e).to_bytes(8, "little"))   # noqa: E731
+    state.previous_justified_checkpoint = mod.Checkpoint(pj, root(pj))
+    state.current_justified_checkpoint = mod.Checkpoint(cj, root(cj))
+    state.finalized_checkpoint = mod.Checkpoint(max(0, pj - 1), root(max(0, pj - 1)))
+    state.justification_bits = [int(b) for b in rng.integers(0, 2, size=4)]
+    return state
+
+
+def ffg_outcome(state):
+    return {"previous_justified": [state.previous_justified_checkpoint.epoch, state.previous_justified_checkpoint.root.hex()],
+            "current_justified": [state.current_justified_checkpoint.epoch, state.current_justified_checkpoint.root.hex()],
+            "finalized": [state.finalized_checkpoint.epoch, state.finalized_checkpoint.root.hex()],
+            "justification_bits": [int(b) for b in state.justification_bits]}

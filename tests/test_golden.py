@@ -87,6 +87,14 @@ def test_oracle_get_head_golden():
         assert spec.get_latest_attesting_balance(store, bytes.fromhex(r)) == w
 
 
+def test_oracle_ffg_golden():
+    spec, state = _state(PKS)
+    for case in G["ffg"]:
+        st = scenarios.ffg_case(copy.deepcopy(state), case["seed"])
+        spec.process_justification_and_finalization(st)
+        assert dict(scenarios.ffg_outcome(st), seed=case["seed"]) == case
+
+
 # ----------------------------------------------------------------------------- the CUDA path against the same vectors
 @pytest.fixture(scope="module")
 def product():
@@ -137,3 +145,15 @@ def test_gpu_get_head_golden(product):
     assert pspec.get_head(store).hex() == G["get_head"]["head"]
     for r, w in G["get_head"]["weights"].items():
         assert pspec.get_weight(store, bytes.fromhex(r)) == w
+
+
+@pytest.mark.gpu
+def test_gpu_ffg_golden(product):
+    """process_justification_and_finalization with the balance sums on the device (b2_ffg_balances) against what the reference's
+    own text produced for the same generated states."""
+    PS, pspec = product
+    _, ostate = _state(PKS)
+    for case in G["ffg"]:
+        st = scenarios.ffg_case(_pstate(PS, copy.deepcopy(ostate)), case["seed"], mod=PS)
+        pspec.process_justification_and_finalization(st)
+        assert dict(scenarios.ffg_outcome(st), seed=case["seed"]) == case

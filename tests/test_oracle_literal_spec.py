@@ -168,3 +168,27 @@ def test_update_latest_messages_literal_vs_numpy(env):
             assert store.latest_messages[v] == S.LatestMessage(int(msg_epoch[v]), rb[msg_block[v]])
         else:
             assert v not in store.latest_messages
+
+
+def test_ffg_literal_vs_oracle(env):
+    """process_justification_and_finalization / weigh_justification_and_finalization: the reference's own text (ref :793-852)
+    against the oracle's restatement on 80 generated end-of-epoch states; every branch must have fired."""
+    import copy
+    spec, state0, ns = env[0], env[1], env[2]
+    seen = set()
+    for seed in range(80):
+        st_ref = scenarios.ffg_case(copy.deepcopy(state0), seed)
+        st_or = copy.deepcopy(st_ref)
+        before = (st_ref.current_justified_checkpoint, st_ref.finalized_checkpoint)
+        ns["process_justification_and_finalization"](st_ref)
+        spec.process_justification_and_finalization(st_or)
+        got, want = scenarios.ffg_outcome(st_or), scenarios.ffg_outcome(st_ref)
+        assert got == want, seed
+        seen.add(("justified_changed", st_ref.current_justified_checkpoint != before[0]))
+        seen.add(("finalized_changed", st_ref.finalized_checkpoint != before[1]))
+        seen.add(("bits", tuple(want["justification_bits"][:2])))
+        if st_ref.finalized_checkpoint != before[1]:
+            seen.add(("finalized_distance", spec.get_current_epoch(st_ref) - st_ref.finalized_checkpoint.epoch))
+    assert {("justified_changed", True), ("justified_changed", False), ("finalized_changed", True), ("finalized_changed", False)} <= seen
+    assert {("bits", (0, 0)), ("bits", (0, 1)), ("bits", (1, 0)), ("bits", (1, 1))} <= seen
+    assert {("finalized_distance", 1), ("finalized_distance", 2), ("finalized_distance", 3)} <= seen
