@@ -89,6 +89,16 @@ int b2_hash_to_g2(b2_ctx* ctx, const uint8_t* msg32, uint32_t n_msg, uint8_t* ou
 /* `hash` of the spec (SHA-256; pos-evolution.md:486, :522, :525), batched over n messages of msg_len bytes each */
 int b2_sha256_batch(b2_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint64_t n, uint8_t* out32);
 
+/* SSZ wire form of n Attestations (pos-evolution.md:714-717, AttestationData :689-697): each is
+ *   [u32 LE offset of aggregation_bits = 228][AttestationData 128 B][signature 96 B][Bitlist bytes, length given by the delimiter bit].
+ * wire = the encodings back to back, woff u32[n+1] their byte offsets.  Outputs per attestation: the bit row (delimiter removed,
+ * zero padded to bits_stride bytes -- the form b2_fast_aggregate_verify / b2_latest_messages_update take), its bit length, the
+ * 128-byte AttestationData record (the input of b2_signing_roots) and the signature.
+ * status_out: 0 ok; 1 malformed container; 2 empty Bitlist / no delimiter; 3 longer than max_bits (MAX_VALIDATORS_PER_COMMITTEE)
+ * or than bits_stride allows.  A rejected attestation yields zero rows: malformed input is data, not an error. */
+int b2_attestations_decode(b2_ctx* ctx, const uint8_t* wire, const uint32_t* woff, uint32_t n, uint32_t bits_stride, uint32_t max_bits,
+                           uint8_t* bits_out, uint32_t* bit_len_out, uint8_t* data128_out, uint8_t* sig96_out, int32_t* status_out);
+
 /* compute_signing_root(AttestationData, domain) (pattern of pos-evolution.md:163; containers :689-697, :219-221) for n attestations:
  * data128 = the 128-byte SSZ serialisation of each AttestationData; domain32 = one 32-byte domain for the batch, or one per
  * attestation when per_attestation_domain != 0.  SSZ merkleization (10 SHA-256 per attestation) runs on the GPU. */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "b2_participation_read": (c_int, [c_void_p, c_int, c_void_p, c_uint64]),
     "b2_participation_update": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_uint32, c_uint64, c_uint64, c_void_p]),
     "b2_ffg_balances": (c_int, [c_void_p, c_uint32, c_void_p]),
+    "b2_attestations_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2_set_fork_choice_params": (c_int, [c_void_p, c_uint64, c_int]),
     "b2_epoch_set_pairing_form": (c_int, [c_void_p, c_int]),
     "b2_on_attester_slashing": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint32]),

@@ -729,6 +729,37 @@ int b2_signing_roots(b2_ctx* ctx, const uint8_t* data128, const uint8_t* domain3
     return B2_OK;
 }
 
+// ------------------------------------------------------------------------------------------ SSZ wire decode (:714-717)
+int b2_attestations_decode(b2_ctx* ctx, const uint8_t* wire, const uint32_t* woff, uint32_t n, uint32_t bits_stride, uint32_t max_bits,
+                           uint8_t* bits_out, uint32_t* bit_len_out, uint8_t* data128_out, uint8_t* sig96_out, int32_t* status_out) {
+    REQUIRE(ctx && wire && woff && n > 0 && bits_stride > 0 && bits_out && bit_len_out && data128_out && sig96_out && status_out,
+            "attestations_decode: bad arguments");
+    REQUIRE(woff[0] == 0, "attestations_decode: woff[0] must be 0");
+    for (uint32_t i = 0; i < n; i++) REQUIRE(woff[i + 1] >= woff[i], "attestations_decode: woff must be non-decreasing");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    const size_t total = woff[n];
+    const size_t o_bits = 0, o_len = o_bits + (((size_t)n * bits_stride + 15) & ~(size_t)15), o_data = o_len + (size_t)n * 4,
+                 o_sig = o_data + (size_t)n * 128, o_st = o_sig + (size_t)n * 96, o_end = o_st + (size_t)n * 4;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_a, total + 16)) || (rc = ensure(ctx, ctx->in_b, (size_t)(n + 1) * 4)) || (rc = ensure(ctx, ctx->out_a, o_end))) return rc;
+    if (total) CK(cudaMemcpyAsync(ctx->in_a.p, wire, total, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_b.p, woff, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+    uint8_t* o = (uint8_t*)ctx->out_a.p;
+    k_attestations_decode<<<blocks_for((uint64_t)n * 32, 128), 128, 0, s>>>((const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, n, bits_stride, max_bits,
+                                                                          o + o_bits, (uint32_t*)(o + o_len), o + o_data, o + o_sig, (int32_t*)(o + o_st));
+    CKL(ctx);
+    std::vector<uint8_t> host(o_end);                       // outputs stay untouched on error
+    CK(cudaMemcpyAsync(host.data(), o, o_end, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(bits_out, host.data() + o_bits, (size_t)n * bits_stride);
+    memcpy(bit_len_out, host.data() + o_len, (size_t)n * 4);
+    memcpy(data128_out, host.data() + o_data, (size_t)n * 128);
+    memcpy(sig96_out, host.data() + o_sig, (size_t)n * 96);
+    memcpy(status_out, host.data() + o_st, (size_t)n * 4);
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------------------------------ committee shuffle
 int b2_shuffle_committees_dev(b2_ctx* ctx, const uint8_t* d_seed32, const uint32_t* d_active, uint32_t n_active, uint32_t rounds,
                               uint32_t* d_members_out, void* stream) {

@@ -790,6 +790,60 @@ __global__ void __launch_bounds__(64) k_signing_roots(const uint8_t* __restrict_
 }
 }  // namespace b2
 
+// ------------------------------------------------------------------------------------------ SSZ wire decode of Attestation
+// Attestation (/root/reference/pos-evolution.md:714-717) on the wire: [u32 offset of aggregation_bits = 228][AttestationData, 128 B]
+// [signature, 96 B][Bitlist[MAX_VALIDATORS_PER_COMMITTEE] bytes].  A Bitlist carries its length as a delimiter: the highest set
+// bit of its last byte (:715); that byte may not be zero.  One warp per attestation: the lanes copy the fixed part, lane 0 finds
+// the delimiter, the lanes write the bit row with the delimiter cleared and zero padding up to bits_stride bytes.
+// status: 0 ok, 1 malformed container (too short / wrong offset), 2 empty bitlist or missing delimiter, 3 more than max_bits bits.
+namespace b2 {
+#define B2_ATT_FIXED 228u
+__global__ void __launch_bounds__(128) k_attestations_decode(const uint8_t* __restrict__ wire, const uint32_t* __restrict__ woff, uint32_t n,
+                                                              uint32_t bits_stride, uint32_t max_bits, uint8_t* bits_out, uint32_t* bit_len_out,
+                                                              uint8_t* data128_out, uint8_t* sig96_out, int32_t* status_out) {
+    const uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (a >= n) return;
+    const uint32_t begin = woff[a], end = woff[a + 1];
+    const uint8_t* w = wire + begin;
+    uint8_t* brow = bits_out + (uint64_t)a * bits_stride;
+    for (uint32_t k = lane; k < bits_stride; k += 32) brow[k] = 0;
+    int32_t st = 0;
+    uint32_t nbits = 0, nbytes = 0;
+    if (end < begin || end - begin < B2_ATT_FIXED) {
+        st = 1;
+    } else {
+        const uint32_t o = (uint32_t)w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16) | ((uint32_t)w[3] << 24);
+        nbytes = end - begin - B2_ATT_FIXED;
+        if (o != B2_ATT_FIXED) {
+            st = 1;
+        } else if (nbytes == 0 || w[end - begin - 1] == 0) {
+            st = 2;
+        } else {
+            const uint32_t last = w[end - begin - 1];
+            const uint32_t top = 31u - (uint32_t)__clz((int)last);          // position of the delimiter bit in the last byte
+            nbits = 8 * (nbytes - 1) + top;
+            if (nbits > max_bits || (nbits + 7) / 8 > bits_stride) st = 3;
+        }
+    }
+    if (st == 0) {
+        for (uint32_t k = lane; k < 128; k += 32) data128_out[128 * (uint64_t)a + k] = w[4 + k];
+        for (uint32_t k = lane; k < 96; k += 32) sig96_out[96 * (uint64_t)a + k] = w[132 + k];
+        const uint32_t full = nbits >> 3;                                   // bytes that carry 8 payload bits
+        __syncwarp();
+        for (uint32_t k = lane; k < full; k += 32) brow[k] = w[B2_ATT_FIXED + k];
+        if (lane == 0 && (nbits & 7u)) brow[full] = w[B2_ATT_FIXED + full] & (uint8_t)((1u << (nbits & 7u)) - 1u);
+    } else {
+        for (uint32_t k = lane; k < 128; k += 32) data128_out[128 * (uint64_t)a + k] = 0;
+        for (uint32_t k = lane; k < 96; k += 32) sig96_out[96 * (uint64_t)a + k] = 0;
+        nbits = 0;
+    }
+    if (lane == 0) {
+        bit_len_out[a] = nbits;
+        status_out[a] = st;
+    }
+}
+}  // namespace b2
+
 // ------------------------------------------------------------------------------------------ participation flags + proposer-reward numerators
 // The bookkeeping loop of process_attestation (/root/reference/pos-evolution.md:745-749): for every attesting index and every
 // flag the attestation earns, set the flag if it is not set yet and credit get_base_reward(index) * weight to THIS

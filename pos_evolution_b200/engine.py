@@ -158,6 +158,21 @@ class Engine:
         self._ck(self.lib.b2_sha256_batch(self.h, _p(m) if msg_len else None, msg_len, n, _p(out)))
         return out
 
+    def attestations_decode(self, wire: bytes, woff, bits_stride: int, max_bits: int):
+        """SSZ wire decode of n Attestations (pos-evolution.md:714-717) -> (bits u8[n][stride], bit_len u32[n], data128 u8[n][128],
+        sig96 u8[n][96], status i32[n])."""
+        woff = _c(woff, np.uint32)
+        n = woff.shape[0] - 1
+        w = np.frombuffer(bytes(wire), dtype=np.uint8) if len(wire) else np.zeros(1, dtype=np.uint8)
+        assert int(woff[-1]) == len(wire)
+        bits = np.zeros((n, bits_stride), dtype=np.uint8)
+        blen = np.zeros(n, dtype=np.uint32)
+        data = np.zeros((n, 128), dtype=np.uint8)
+        sig = np.zeros((n, 96), dtype=np.uint8)
+        st = np.zeros(n, dtype=np.int32)
+        self._ck(self.lib.b2_attestations_decode(self.h, _p(w), _p(woff), n, int(bits_stride), int(max_bits), _p(bits), _p(blen), _p(data), _p(sig), _p(st)))
+        return bits, blen, data, sig, st
+
     def signing_roots(self, data128, domains32):
         """compute_signing_root for n attestations: data128 uint8[n,128] (SSZ-serialised AttestationData), domains32 uint8[32] or uint8[n,32]."""
         d = _c(data128, np.uint8).reshape(-1, 128)

@@ -182,6 +182,20 @@ def serialize_attestation_data(d: AttestationData) -> bytes:
             + int(d.source.epoch).to_bytes(8, "little") + bytes(d.source.root) + int(d.target.epoch).to_bytes(8, "little") + bytes(d.target.root))
 
 
+def deserialize_attestation_data(b: bytes) -> AttestationData:
+    u = lambda o: int.from_bytes(b[o:o + 8], "little")       # noqa: E731
+    return AttestationData(slot=u(0), index=u(8), beacon_block_root=bytes(b[16:48]), source=Checkpoint(u(48), bytes(b[56:88])),
+                           target=Checkpoint(u(88), bytes(b[96:128])))
+
+
+def serialize_attestation(att: Attestation) -> bytes:
+    """SSZ wire form (:714-717): [offset of aggregation_bits = 228][data][signature][Bitlist with its delimiter bit]."""
+    n = len(att.aggregation_bits)
+    bl = bytearray(pack_bits([list(att.aggregation_bits)], stride=n // 8 + 1)[0].tobytes())
+    bl[n >> 3] |= 1 << (n & 7)
+    return (228).to_bytes(4, "little") + serialize_attestation_data(att.data) + bytes(att.signature) + bytes(bl)
+
+
 def compute_domain(domain_type: bytes, fork_version: bytes, genesis_validators_root: bytes) -> bytes:
     fork_data_root = _merkle([bytes(fork_version) + bytes(28), bytes(genesis_validators_root)])
     return bytes(domain_type) + fork_data_root[:28]
@@ -390,6 +404,26 @@ class Spec:
     @staticmethod
     def compute_signing_root(data: AttestationData, domain):
         return _merkle([hash_tree_root_attestation_data(data), bytes(domain)])
+
+    # ------------------------------------------------------------------ SSZ wire decode on the device (:714-717)
+    def decode_attestations(self, encodings):
+        """List of SSZ-encoded Attestations -> list of Attestation (None where the encoding is malformed: no delimiter bit, more
+        than MAX_VALIDATORS_PER_COMMITTEE bits, truncated container).  One GPU call for the batch (b2_attestations_decode); the
+        same call yields the bit rows and the 128-byte data records the verification kernels take."""
+        if not encodings:
+            return []
+        limit = self.p.MAX_VALIDATORS_PER_COMMITTEE
+        off = np.zeros(len(encodings) + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(e) for e in encodings])
+        bits, blen, data, sig, st = self.engine.attestations_decode(b"".join(bytes(e) for e in encodings), off, (limit + 7) // 8, limit)
+        out = []
+        for a in range(len(encodings)):
+            if st[a] != 0:
+                out.append(None)
+                continue
+            row = np.unpackbits(bits[a], bitorder="little")[:int(blen[a])]
+            out.append(Attestation([bool(x) for x in row], deserialize_attestation_data(data[a].tobytes()), sig[a].tobytes()))
+        return out
 
     # ------------------------------------------------------------------ registry on the device
     def sync_registry(self, state):

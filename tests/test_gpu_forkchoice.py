@@ -166,3 +166,45 @@ def test_fork_choice_variants_expiry_slashed_equivocation(eng):
     assert len(np.intersect1d(a1, a2)) > 0
     w_ref = fast.ghost_weights(parent, msg_block, has_msg, eff, active, eq2, -1, 0)
     assert np.array_equal(eng.get_weights(), w_ref)
+
+
+def test_attestations_wire_decode_matches_oracle(eng):
+    """b2_attestations_decode (SSZ wire form of Attestation, pos-evolution.md:714-717) against the oracle's (de)serialiser:
+    every bit length around the byte boundaries up to MAX_VALIDATORS_PER_COMMITTEE, random payloads, and the malformed shapes
+    (no delimiter, empty bitlist, too long, wrong offset, truncated)."""
+    from oracle import ssz
+    rng = np.random.default_rng(9)
+    limit, stride = 2048, 256
+    lengths = list(range(0, 20)) + [63, 64, 65, 511, 512, 513, 2040, 2047, 2048] + [int(x) for x in rng.integers(1, 2049, size=60)]
+    enc, want = [], []
+    for n in lengths:
+        bits = [bool(b) for b in rng.integers(0, 2, size=n)]
+        data, sig = bytes(rng.integers(0, 256, size=128, dtype=np.uint8)), bytes(rng.integers(0, 256, size=96, dtype=np.uint8))
+        e = ssz.serialize_attestation(bits, data, sig)
+        assert ssz.deserialize_attestation(e, limit) == (bits, data, sig)
+        enc.append(e)
+        want.append((0, bits, data, sig))
+    good = enc[30]
+    bad = [(good[:-1] + b"\x00", 2),                                        # last byte zero: no delimiter
+           (good[:228], 2),                                                 # empty bitlist
+           (ssz.serialize_attestation([True] * 2049, bytes(128), bytes(96)), 3),   # one bit over the limit
+           (b"\xe5" + good[1:], 1),                                         # wrong offset
+           (good[:100], 1),                                                 # truncated container
+           (b"", 1)]
+    for e, code in bad:
+        try:
+            ssz.deserialize_attestation(e, limit)
+            raise AssertionError("oracle accepted a malformed encoding")
+        except ValueError:
+            pass
+        enc.append(e)
+        want.append((code, [], bytes(128), bytes(96)))
+    off = np.zeros(len(enc) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(e) for e in enc])
+    bits, blen, data, sig, st = eng.attestations_decode(b"".join(enc), off, stride, limit)
+    for a, (code, wbits, wdata, wsig) in enumerate(want):
+        assert int(st[a]) == code, a
+        assert int(blen[a]) == len(wbits), a
+        row = np.unpackbits(bits[a], bitorder="little")
+        assert [bool(x) for x in row[:len(wbits)]] == wbits and not row[len(wbits):].any(), a
+        assert data[a].tobytes() == wdata and sig[a].tobytes() == wsig, a

@@ -177,3 +177,25 @@ def test_on_attester_slashing_marks_equivocators(env):
     with pytest.raises(AssertionError):
         pspec.on_attester_slashing(store2, PS.AttesterSlashing(ia[0], bad))
     assert store2.equivocating_indices == set()
+
+
+def test_decode_attestations_roundtrip(env):
+    """Spec.decode_attestations(serialize_attestation(a)) == a for real (signed) attestations, through the device decode
+    (b2_attestations_decode); the decoded objects are processed like the originals; a malformed encoding comes back as None; and
+    the product's encoder agrees with the oracle's."""
+    from oracle import ssz
+    ospec, ostate, pspec, PS, PB, pks = env
+    atts = [_to_product(PS, scenarios.make_attestation(ospec, ostate, 8, 0)),
+            _to_product(PS, scenarios.make_attestation(ospec, ostate, 8, 1, bits=[True, False, True, True])),
+            _to_product(PS, scenarios.make_attestation(ospec, ostate, 5, 1))]
+    enc = [PS.serialize_attestation(a) for a in atts]
+    for a, e in zip(atts, enc):
+        assert e == ssz.serialize_attestation(list(a.aggregation_bits), PS.serialize_attestation_data(a.data), bytes(a.signature))
+    got = pspec.decode_attestations(enc + [enc[0][:-1] + b"\x00"])
+    assert got[3] is None
+    for a, g in zip(atts, got[:3]):
+        assert list(g.aggregation_bits) == list(a.aggregation_bits) and g.data == a.data and bytes(g.signature) == bytes(a.signature)
+    sp, sq = _state_to_product(PS, ostate), _state_to_product(PS, ostate)
+    pspec.process_attestations(sp, got[:3])
+    pspec.process_attestations(sq, atts)
+    assert sp.balances == sq.balances and sp.current_epoch_participation == sq.current_epoch_participation
