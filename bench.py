@@ -7,9 +7,11 @@ One step = one full epoch for the 2^20 validators a rank owns (BASELINE.json con
 2 048 aggregates, FastAggregateVerify of the 2 048 aggregates (registry-indexed pubkey gather,
 hash-to-G2, pairing), update_latest_messages for the accepted ones, vote-weight scatter, [NCCL
 all-reduce of u64[10 000] vote weights when N > 1], get_head on a 10 000-block tree.
-`value`  = attestations/s with every input resident in HBM; `e2e` = the same through
-EpochProcessor.process_epoch_host with pinned HOST buffers (H2D of the signatures/bits/messages and
-D2H of verdicts + head inside the timed region).  Weak scaling: every rank owns its own 2^20
+`value`  = attestations/s with every input resident in HBM, K epochs through the depth-3 software
+pipeline (EpochProcessor.submit_dev; all K results complete inside the timed region); `e2e` = the same
+through EpochProcessor.submit_host with pinned HOST buffers (H2D of the signatures/bits/messages and D2H
+of verdicts + head of every epoch inside the timed region); `ms_per_step_unpipelined` = one epoch at a
+time (process_epoch_dev).  Weak scaling: every rank owns its own 2^20
 validators (N x 2^20 validators overall); the only exchange is the vote-weight all-reduce.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo, on the GPU(s)
