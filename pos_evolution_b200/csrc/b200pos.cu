@@ -45,6 +45,7 @@ struct b2_ctx {
     // threads per block of the thread-per-aggregate kernels when they run under the epoch pipeline (see launch_miller)
     unsigned tail_block = 128;
     bool epoch_team = false;   // b2_epoch_set_pairing_form
+    unsigned k2_block = 32;    // threads per aggregate of k_g1_aggregate under the epoch pipeline (B2_K2_BLOCK: 32/64/128)
     int pairing_form = 0;      // 0: team kernels for the synchronous calls, thread-per-aggregate under the pipeline; 1: always team; 2: always thread
     // threads per block of k_g2_decompress: its blocks fill the register file, so a smaller block is what a pairing warp of the
     // previous epoch displaces when the two overlap
@@ -150,6 +151,10 @@ int b2_init(int device, b2_ctx** out) {
     if (const char* e = getenv("B2_TAIL_BLOCK")) {          // tuning knob (32/64/128); the default is the measured best
         unsigned v = (unsigned)atoi(e);
         if (v == 32 || v == 64 || v == 128) ctx->tail_block = v;
+    }
+    if (const char* e = getenv("B2_K2_BLOCK")) {
+        unsigned v = (unsigned)atoi(e);
+        if (v == 32 || v == 64 || v == 128) ctx->k2_block = v;
     }
     if (const char* e = getenv("B2_PAIRING_FORM")) ctx->pairing_form = !strcmp(e, "team") ? 1 : (!strcmp(e, "thread") ? 2 : 0);
     if (const char* e = getenv("B2_RESERVE_SMS")) {
@@ -477,8 +482,11 @@ static int verify_fork(b2_ctx* ctx, vslot& V, const pk_source& P, const uint8_t*
                                                           (uint32_t*)V.pkjac.p, (uint8_t*)V.pkst.p);
         CKL(ctx);
     } else {
-        k_g1_aggregate<<<n_agg, 128, 0, ctx->s_aux[1]>>>(ctx->d_records, ctx->d_valid, P.d_members, P.d_off, P.d_bits, P.bits_stride, n_agg,
-                                                        (uint32_t*)V.pkjac.p, (uint8_t*)V.pkst.p);
+        // one block per aggregate.  128 threads when the caller waits; ONE WARP under the epoch pipeline: the 5-round shuffle tree costs
+        // every warp 80 Fp multiplications whatever its share of the 512 records, so 4 warps spend 2.1x the multiply-pipe time of one
+        const unsigned k2_block = team ? 128u : ctx->k2_block;
+        k_g1_aggregate<<<n_agg, k2_block, 0, ctx->s_aux[1]>>>(ctx->d_records, ctx->d_valid, P.d_members, P.d_off, P.d_bits, P.bits_stride, n_agg,
+                                                             (uint32_t*)V.pkjac.p, (uint8_t*)V.pkst.p);
         CKL(ctx);
     }
     CK(cudaStreamWaitEvent(ctx->s_aux[1], V.ev_join0, 0));
