@@ -104,3 +104,62 @@ def test_store_to_arrays_topological():
     assert sorted(order) == sorted(rb) and order[0] == rb[0]
     for i in range(1, 60):
         assert p2[i] < i and order[p2[i]] == store.blocks[order[i]].parent_root
+
+
+def test_ffg_host_logic_matches_oracle():
+    """The scalar half of process_justification_and_finalization in the product (2/3 tests, bit shifting, the four finalization rules;
+    pos-evolution.md:817-852) against the oracle on 80 generated end-of-epoch states.  The balance sums come from a stand-in for
+    b2_ffg_balances here (the kernel itself is checked on the GPU, tests/test_gpu_participation.py)."""
+    import copy
+    from pos_evolution_b200 import spec as PS
+    ospec, ostate = scenarios.minimal_state(64, slot=9, pks=[bytes(48)] * 64)
+
+    class _SumsOnly:                                    # Engine stand-in: the three sums computed on the host from what was "uploaded"
+        def registry_load(self, pk, eff, flags):
+            self.eff, self.flags = np.asarray(eff, dtype=np.uint64), np.asarray(flags, dtype=np.uint8)
+
+        registry_update_balances = lambda self, eff, flags: self.registry_load(None, eff, flags)     # noqa: E731
+
+        def participation_load(self, which, table):
+            self.__dict__.setdefault("part", {})[which] = np.asarray(table, dtype=np.uint8)
+
+        def ffg_balances(self, flag):
+            act, sl, actp = (self.flags & 1) != 0, (self.flags & 2) != 0, (self.flags & 4) != 0
+            s = lambda m: int(self.eff[m].astype(object).sum()) if m.any() else 0                   # noqa: E731
+            cur, prev = (((self.part[w] >> flag) & 1) != 0 for w in (0, 1))
+            return s(act), s(act & ~sl & cur), s(actp & ~sl & prev), s(act & ~sl)
+
+    ps = PS.Spec(PS.MINIMAL, engine=_SumsOnly())
+    for seed in range(80):
+        so = scenarios.ffg_case(copy.deepcopy(ostate), seed)
+        sp = PS.BeaconState(
+            slot=so.slot, fork=PS.Fork(so.fork.previous_version, so.fork.current_version, so.fork.epoch),
+            genesis_validators_root=so.genesis_validators_root,
+            validators=[PS.Validator(v.pubkey, v.effective_balance, v.slashed, v.activation_epoch, v.exit_epoch) for v in so.validators],
+            balances=list(so.balances), randao_mixes=list(so.randao_mixes), block_roots=list(so.block_roots),
+            previous_epoch_participation=list(so.previous_epoch_participation), current_epoch_participation=list(so.current_epoch_participation),
+            previous_justified_checkpoint=PS.Checkpoint(so.previous_justified_checkpoint.epoch, so.previous_justified_checkpoint.root),
+            current_justified_checkpoint=PS.Checkpoint(so.current_justified_checkpoint.epoch, so.current_justified_checkpoint.root),
+            finalized_checkpoint=PS.Checkpoint(so.finalized_checkpoint.epoch, so.finalized_checkpoint.root),
+            justification_bits=list(so.justification_bits))
+        ospec.process_justification_and_finalization(so)
+        ps.process_justification_and_finalization(sp)
+        assert scenarios.ffg_outcome(sp) == scenarios.ffg_outcome(so), seed
+
+
+def test_attestation_wire_form_matches_oracle():
+    """serialize_attestation / deserialize_attestation_data of the product against the oracle's SSZ (de)serialiser."""
+    from oracle import ssz
+    from pos_evolution_b200 import spec as PS
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 8, 9, 63, 64, 512, 2048):
+        bits = [bool(b) for b in rng.integers(0, 2, size=n)]
+        data = PS.AttestationData(int(rng.integers(1 << 40)), int(rng.integers(64)), bytes(rng.integers(0, 256, 32, dtype=np.uint8)),
+                                  PS.Checkpoint(int(rng.integers(1 << 30)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))),
+                                  PS.Checkpoint(int(rng.integers(1 << 30)), bytes(rng.integers(0, 256, 32, dtype=np.uint8))))
+        sig = bytes(rng.integers(0, 256, 96, dtype=np.uint8))
+        enc = PS.serialize_attestation(PS.Attestation(bits, data, sig))
+        d128 = PS.serialize_attestation_data(data)
+        assert enc == ssz.serialize_attestation(bits, d128, sig)
+        got_bits, got_data, got_sig = ssz.deserialize_attestation(enc, 2048)
+        assert got_bits == bits and got_sig == sig and PS.deserialize_attestation_data(got_data) == data
