@@ -42,18 +42,21 @@ struct b2_ctx {
     uint32_t* d_lmd_block = nullptr;
     uint8_t* d_equiv = nullptr;
     // fork-choice variants: votes older than fc_min_key (epoch << 32) expire; v1.3 get_weight skips slashed validators
-    unsigned long long fc_min_key = 0;
-    int fc_exclude_slashed = 0;
-    // ---- launch shapes of the epoch pipeline (defaults = the measured best, profiles/README.md; B2_* environment knobs override)
-    unsigned tail_block = 128;   // threads per block of the thread-per-aggregate kernels under the pipeline (see launch_miller)
-    unsigned k2_block = 32;      // threads per aggregate of k_g1_aggregate under the pipeline
-    unsigned dec_block = 128;    // threads per block of k_g2_decompress (4 blocks of 128 fill the register file of an SM)
-    bool epoch_team = false;     // b2_epoch_set_pairing_form
-    int pairing_form = 0;        // B2_PAIRING_FORM: 0 team kernels where the caller waits, thread kernels under the pipeline; 1 team; 2 thread
-    // SMs the persistent decompression kernel leaves empty for the pairing tails (kernels.cuh); 0 = off (measured slower)
+    // threads per block of the thread-per-aggregate kernels when they run under the epoch pipeline (see launch_miller)
+    unsigned tail_block = 128;
+    bool epoch_team = false;   // b2_epoch_set_pairing_form
+    unsigned k2_block = 32;    // threads per aggregate of k_g1_aggregate under the epoch pipeline (B2_K2_BLOCK: 32/64/128)
+    int pairing_form = 0;      // 0: team kernels for the synchronous calls, thread-per-aggregate under the pipeline; 1: always team; 2: always thread
+    // threads per block of k_g2_decompress: its blocks fill the register file, so a smaller block is what a pairing warp of the
+    // previous epoch displaces when the two overlap
+    unsigned dec_block = 128;
+    // SMs the persistent decompression kernel of the pipelined epoch path leaves empty for the pairing tails (kernels.cuh).
+    // 0 = off (the default: measured slower); B2_RESERVE_SMS=n turns the experiment on.
     unsigned reserve_sms = 0;
     sm_mask reserved = {{0, 0, 0, 0}};
     unsigned long long* d_dec_counter = nullptr;      // one work counter per epoch slot
+    unsigned long long fc_min_key = 0;
+    int fc_exclude_slashed = 0;
     // epoch participation flags (0 = current, 1 = previous) and the per-(validator, flag) election table
     uint32_t* d_part[2] = {nullptr, nullptr};
     uint32_t* d_part_first = nullptr;
