@@ -97,7 +97,7 @@ def run_reference(args):
     sample = "%d committees x %d members per step (1 per core): bls.Aggregate + FastAggregateVerify" % (cores, COMMITTEE_SIZE)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fp)",
+        "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "python int (381-bit Fp, the oracle's arbitrary-precision arithmetic)",
         "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
