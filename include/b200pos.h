@@ -38,7 +38,7 @@ enum {
 };
 
 /* status bits written by b2_g1_aggregate (why py_ecc's FastAggregateVerify would return False) */
-enum { B2_PK_OK = 0, B2_PK_INVALID_KEY = 1, B2_PK_EMPTY = 2, B2_PK_INFINITY = 4 };
+enum { B2_PK_OK = 0, B2_PK_INVALID_KEY = 1, B2_PK_EMPTY = 2, B2_PK_INFINITY = 4, B2_PK_BAD_INDEX = 8 };
 
 int b2_init(int device, b2_ctx** out);
 void b2_destroy(b2_ctx* ctx);
@@ -151,6 +151,15 @@ int b2_ffg_balances(b2_ctx* ctx, uint32_t flag_index, uint64_t* out4);
  * b2_on_attester_slashing: the validators present in BOTH sorted index lists become equivocating (Store.equivocating_indices)
  *   and stop counting; validity of the slashing itself (:1453-1457) is the caller's job. */
 int b2_set_fork_choice_params(b2_ctx* ctx, uint64_t min_vote_epoch, int exclude_slashed);
+/* How bls.FastAggregateVerify (is_valid_indexed_attestation, pos-evolution.md:736/:976) is evaluated for a BATCH of aggregates:
+ *   mode 0 (default): e(PK_a, H(m_a)) * e(-g1, S_a) == 1 for every aggregate a (two Miller loops + one final exponentiation each);
+ *   mode 1: random-linear-combination batches -- per group of 32 aggregates ONE equation
+ *           prod_a e([r_a] PK_a, H(m_a)) * e(-g1, sum_a [r_a] S_a) == 1, r_a = 64-bit scalars derived by SHA-256 from `seed32`
+ *           (the verifier's secret: pass fresh randomness), i.e. one Miller loop per aggregate plus one Miller loop and one final
+ *           exponentiation per group; the members of a group whose equation fails are then verified one by one, so ok_out is
+ *           the mode-0 vector (a wrong accept needs a 2^-63 coincidence).  Less work, longer critical path: for bulk verification.
+ * Synchronises the device.  Applies to every FastAggregateVerify / epoch entry point of the context. */
+int b2_set_verify_mode(b2_ctx* ctx, int mode, const uint8_t* seed32);
 int b2_on_attester_slashing(b2_ctx* ctx, const uint32_t* indices_1, uint32_t n1, const uint32_t* indices_2, uint32_t n2);
 
 /* Store.blocks (pos-evolution.md:898) as arrays in topological order (parent[b] < b, parent[0] ignored; block 0 =
@@ -162,12 +171,27 @@ int b2_get_weights(b2_ctx* ctx, int32_t boost_idx, uint64_t boost_score, uint64_
 /* get_head (pos-evolution.md:1102-1116): index of the head block */
 int b2_get_head(b2_ctx* ctx, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score, uint32_t* head_idx_out);
 
-/* ---- device-pointer entry points (asynchronous on `stream`) ------------------------------------------------------ */
+/* ---- device-pointer entry points (asynchronous on `stream`) ------------------------------------------------------
+ * The host cannot read what device pointers point to, so the checks the host entry points make before touching anything
+ * (check_batch: monotone offsets, rows no longer than the bit row, member indices inside the registry, epochs < 2^32 - 1) are made by
+ * the kernels themselves: an offending aggregate is skipped -- it fails verification (status B2_PK_BAD_INDEX), joins no LMD update,
+ * its segment is reported undecodable -- nothing is read or written out of bounds, and the event is recorded in a guard word.
+ * Precondition that cannot be checked on the device: off[n_agg] <= length of the members array.
+ * b2_guard_flags: synchronises, returns and clears that word (bit0 member index >= n_validators, bit1 malformed offsets row,
+ * bit2 target epoch does not fit 32 bits). */
+enum { B2_GUARD_BAD_INDEX = 1, B2_GUARD_BAD_ROW = 2, B2_GUARD_BAD_EPOCH = 4 };
+int b2_guard_flags(b2_ctx* ctx, uint32_t* flags_out);
 int b2_aggregate_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig, uint8_t* d_out96,
                      int32_t* d_seg_status, void* stream);
 int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                                  uint32_t bits_stride, const uint8_t* d_msg32, const uint8_t* d_sig96, uint32_t n_agg,
                                  uint8_t* d_ok_out, void* stream);
+/* The gather stage of K2 alone, for measurement (north_star: ">= 60 % of HBM-read roofline on the pubkey gather"): for every aggregate
+ * the XOR of the 24 record words of each selected member's pubkey record (get_attesting_indices + the pubkey list of
+ * is_valid_indexed_attestation, pos-evolution.md:736/:745, without the additions).  form 1 = TMA-staged (cp.async.bulk -> shared
+ * memory -> 128-bit LDS, the path b2_fast_aggregate_verify uses), form 0 = plain 128-bit global loads.  Both give the same words. */
+int b2_gather_probe_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
+                        uint32_t n_agg, int form, uint32_t* d_checksum_out, void* stream);
 /* One epoch of this rank in one call: bls.Aggregate per committee (segment a = signatures [off[a], off[a+1]), one per member, in
  * committee order) -> FastAggregateVerify of the aggregates -> update_latest_messages for the accepted ones.  The pubkey/hash half
  * of the verification is overlapped with the signature decompression on side streams. */
@@ -179,12 +203,15 @@ int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members,
  *                             the slot's previous tail has drained);
  *   b2_epoch_tail_dev(slot)   on the slot's own high-priority stream: inversion + compress, subgroup check, second Miller loop,
  *                             final exponentiation, update_latest_messages (applied in epoch order).  Its outputs (aggregate
- *                             signatures, verdicts, the LMD table) are valid for a stream only after b2_epoch_wait_dev(slot, it);
+ *                             signatures, verdicts, the LMD table) are valid for a stream only after b2_epoch_wait_dev(slot, it).
+ *                             d_target_epoch == d_block_idx == NULL: no LMD update in the tail -- the form of a SHARDED epoch (one
+ *                             validator set, committees split over ranks by slot, pos-evolution.md:455), whose caller all-gathers
+ *                             the verdicts and then applies b2_latest_messages_update_dev for ALL aggregates on every rank;
  *   fork choice of epoch k    b2_epoch_wait_dev(slot, s); b2_vote_weights_dev(s); all-reduce; b2_head_from_votes_dev(s) -- enqueue it
  *                             before the tail of epoch k+1, whose LMD update waits for the vote scatter issued before it.
  * The latency-bound tails of epochs k, k-1, .. thereby overlap with each other and with the grid-filling signature decompression of
  * epoch k+1: under that contention one tail takes longer than one decompression, so depth 3 is what keeps the multiply pipe busy. */
-#define B2_EPOCH_SLOTS 4
+#define B2_EPOCH_SLOTS 8
 int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                        uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, void* stream);
 int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
@@ -201,6 +228,9 @@ int b2_latest_messages_update_dev(b2_ctx* ctx, const uint32_t* d_members, const 
 /* direct (un-propagated) vote weight per block in tree pre-order, u64[n_blocks]: the quantity that is summed across
  * GPUs (ncclAllReduce sum, u64) when validators are sharded; then b2_head_from_votes_dev finishes on every rank. */
 int b2_vote_weights_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, void* stream);
+/* the same for the validators [v_begin, v_end) only: the get_head shard of one rank when ONE validator set is spread over the GPUs of
+ * a box (BASELINE.json configs 4/5: N/8 validators per GPU, u64[n_blocks] all-reduce, head on every rank; pos-evolution.md:1102-1116) */
+int b2_vote_weights_range_dev(b2_ctx* ctx, uint64_t v_begin, uint64_t v_end, uint64_t* d_votes_preorder, void* stream);
 int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
                            uint64_t* d_weight_out /* may be NULL */, uint32_t* d_head_idx_out, void* stream);
 uint32_t b2_tree_size(b2_ctx* ctx);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "b2_ffg_balances": (c_int, [c_void_p, c_uint32, c_void_p]),
     "b2_attestations_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2_set_fork_choice_params": (c_int, [c_void_p, c_uint64, c_int]),
+    "b2_set_verify_mode": (c_int, [c_void_p, c_int, c_void_p]),
     "b2_epoch_set_pairing_form": (c_int, [c_void_p, c_int]),
     "b2_on_attester_slashing": (c_int, [c_void_p, c_void_p, c_uint32, c_void_p, c_uint32]),
     "b2_tree_load": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32]),
@@ -65,6 +66,9 @@ SIGNATURES = {
     "b2_epoch_tail_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
     "b2_epoch_wait_dev": (c_int, [c_void_p, c_int, c_void_p]),
     "b2_vote_weights_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "b2_vote_weights_range_dev": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]),
+    "b2_guard_flags": (c_int, [c_void_p, c_void_p]),
+    "b2_gather_probe_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_int, c_void_p, c_void_p]),
     "b2_head_from_votes_dev": (c_int, [c_void_p, c_void_p, c_uint32, c_int32, c_uint64, c_void_p, c_void_p, c_void_p]),
     "b2_tree_size": (c_uint32, [c_void_p]),
 }

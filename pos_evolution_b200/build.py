@@ -23,7 +23,7 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--shared",
-           "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-o", OUT, SRC]
+           "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-o", OUT, SRC, "-ldl"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.check_call(cmd)

@@ -1,7 +1,10 @@
 // b200pos.cu -- C ABI (include/b200pos.h) over the kernels in kernels.cuh.  Single translation
 // unit -> libb200pos.so (nvcc -gencode arch=compute_100a,code=sm_100a).  No CPU fallback anywhere.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: every C-ABI call is a named range in Nsight Systems / ncu --nvtx timelines
 
 #include <algorithm>
 #include <new>
@@ -9,6 +12,8 @@
 
 #include "../../include/b200pos.h"
 #include "kernels.cuh"
+#include "gather.cuh"
+#include "rlc.cuh"
 
 using namespace b2;
 
@@ -19,15 +24,20 @@ struct dbuf {
 
 struct vslot {
     dbuf haff, hflag, pkjac, pkst, saff, sflag, f, sumjac;
-    cudaEvent_t ev_join0 = nullptr, ev_join1 = nullptr, ev_seg = nullptr, ev_tail_done = nullptr;
+    dbuf pkjac_r, rscal, sg_aff, sg_flag, f_g, gpass;      // RLC batch mode: [r]PK, r, per-group signature sums, group Miller values / verdicts
+    cudaEvent_t ev_join0 = nullptr, ev_join1 = nullptr, ev_seg = nullptr, ev_tail_done = nullptr, ev_fork = nullptr;
     cudaStream_t s_tail = nullptr;      // the slot's own tail stream: tails of consecutive epochs overlap each other
+    // the slot's own side streams (hash-to-G2; pubkey aggregation + first Miller loop).  With ONE pair shared by all slots the
+    // latency-bound side chains of consecutive epochs serialise (6 + 10 ms per epoch) -- invisible behind a 32 ms decompression,
+    // but the bound of the step once an epoch is sharded over 8 GPUs and its decompression takes 3.7 ms.
+    cudaStream_t s_aux[2] = {nullptr, nullptr};
 };
 
 struct b2_ctx {
     int device = 0;
     int n_sm = 148;
-    cudaStream_t s_main = nullptr, s_aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_votes_done = nullptr, ev_lmd_done = nullptr;
+    cudaStream_t s_main = nullptr;
+    cudaEvent_t ev_votes_done = nullptr, ev_lmd_done = nullptr;
     vslot slot[B2_EPOCH_SLOTS];
     char err[512] = {0};
     uint64_t launches = 0;
@@ -46,6 +56,12 @@ struct b2_ctx {
     unsigned tail_block = 128;
     bool epoch_team = false;   // b2_epoch_set_pairing_form
     unsigned k2_block = 32;    // threads per aggregate of k_g1_aggregate under the epoch pipeline (B2_K2_BLOCK: 32/64/128)
+    // K2 through the TMA-staged gather kernel (gather.cuh) instead of the LDG form; B2_K2_TMA=0 selects the LDG form (A/B, profiles/)
+    bool k2_tma = true;
+    // FastAggregateVerify mode: 0 = one pairing check per aggregate; 1 = random-linear-combination batches of B2_RLC_GROUP
+    // aggregates with per-aggregate fallback (b2_set_verify_mode); d_rlc_seed = the verifier's secret 32-byte seed
+    int verify_mode = 0;
+    uint8_t* d_rlc_seed = nullptr;
     int pairing_form = 0;      // 0: team kernels for the synchronous calls, thread-per-aggregate under the pipeline; 1: always team; 2: always thread
     // threads per block of k_g2_decompress: its blocks fill the register file, so a smaller block is what a pairing warp of the
     // previous epoch displaces when the two overlap
@@ -55,6 +71,7 @@ struct b2_ctx {
     unsigned reserve_sms = 0;
     sm_mask reserved = {{0, 0, 0, 0}};
     unsigned long long* d_dec_counter = nullptr;      // one work counter per epoch slot
+    uint32_t* d_guard = nullptr;                      // device-side input guard word (kernels.cuh GuardBits), read by b2_guard_flags
     unsigned long long fc_min_key = 0;
     int fc_exclude_slashed = 0;
     // epoch participation flags (0 = current, 1 = previous) and the per-(validator, flag) election table
@@ -69,6 +86,12 @@ struct b2_ctx {
     dbuf sc_pkjac, sc_pkst, sc_haff, sc_hflag, sc_g2aff, sc_g2st, sc_rec, sc_val;
     dbuf in_a, in_b, in_c, in_d, in_e, in_f, in_g, out_a, out_b, sc_shuf, sc_pivot;
 };
+
+struct nvtx_scope {
+    explicit nvtx_scope(const char* name) { nvtxRangePushA(name); }
+    ~nvtx_scope() { nvtxRangePop(); }
+};
+#define B2_NVTX nvtx_scope nvtx_scope_(__func__)
 
 static int fail_cuda(b2_ctx* c, cudaError_t e, const char* what) {
     if (c) snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
@@ -117,8 +140,13 @@ static inline unsigned blocks_for(uint64_t n, unsigned t) { return (unsigned)((n
 extern "C" {
 
 int b2_init(int device, b2_ctx** out) {
+    B2_NVTX;
     if (!out) return B2_EINVAL;
     *out = nullptr;
+    // 8 pipeline slots x (tail + 2 side streams) + main/copy/fork-choice streams: more streams than the default 8 hardware queues,
+    // whose aliasing creates false dependencies between slots.  Only effective when this is the first CUDA call of the process
+    // (bench.py and the package __init__ also set it before torch initialises CUDA).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return B2_ENODEVICE;
     cudaDeviceProp prop;
@@ -136,17 +164,20 @@ int b2_init(int device, b2_ctx** out) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaError_t e = cudaStreamCreateWithPriority(&ctx->s_main, cudaStreamNonBlocking, prio_lo);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithPriority(&ctx->s_aux[i], cudaStreamNonBlocking, prio_hi);
-    for (int i = 0; i < B2_EPOCH_SLOTS && e == cudaSuccess; i++) e = cudaStreamCreateWithPriority(&ctx->slot[i].s_tail, cudaStreamNonBlocking, prio_hi);
+    for (int i = 0; i < B2_EPOCH_SLOTS && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithPriority(&ctx->slot[i].s_tail, cudaStreamNonBlocking, prio_hi);
+        for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaStreamCreateWithPriority(&ctx->slot[i].s_aux[k], cudaStreamNonBlocking, prio_hi);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_lmd_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_votes_done, cudaEventDisableTiming);
     for (int i = 0; i < B2_EPOCH_SLOTS && e == cudaSuccess; i++) {
-        cudaEvent_t* evs[4] = {&ctx->slot[i].ev_join0, &ctx->slot[i].ev_join1, &ctx->slot[i].ev_seg, &ctx->slot[i].ev_tail_done};
-        for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(evs[k], cudaEventDisableTiming);
+        cudaEvent_t* evs[5] = {&ctx->slot[i].ev_join0, &ctx->slot[i].ev_join1, &ctx->slot[i].ev_seg, &ctx->slot[i].ev_tail_done, &ctx->slot[i].ev_fork};
+        for (int k = 0; k < 5 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(evs[k], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_votes_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_g1_gather_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)sizeof(gather_ws));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_g1_gather_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)sizeof(gather_ws));
     ctx->n_sm = prop.multiProcessorCount;
     if (const char* e = getenv("B2_TAIL_BLOCK")) {          // tuning knob (32/64/128); the default is the measured best
         unsigned v = (unsigned)atoi(e);
@@ -156,6 +187,7 @@ int b2_init(int device, b2_ctx** out) {
         unsigned v = (unsigned)atoi(e);
         if (v == 32 || v == 64 || v == 128) ctx->k2_block = v;
     }
+    if (const char* e = getenv("B2_K2_TMA")) ctx->k2_tma = atoi(e) != 0;
     if (const char* e = getenv("B2_PAIRING_FORM")) ctx->pairing_form = !strcmp(e, "team") ? 1 : (!strcmp(e, "thread") ? 2 : 0);
     if (const char* e = getenv("B2_RESERVE_SMS")) {
         unsigned v = (unsigned)atoi(e);
@@ -163,6 +195,10 @@ int b2_init(int device, b2_ctx** out) {
     }
     if (ctx->reserve_sms >= (unsigned)ctx->n_sm / 2) ctx->reserve_sms = ctx->n_sm / 9;
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_dec_counter, sizeof(unsigned long long) * B2_EPOCH_SLOTS);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_rlc_seed, 32);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_rlc_seed, 0, 32);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_guard, 256);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_guard, 0, 256);
     if (e == cudaSuccess && ctx->reserve_sms > 0) {
         // the SM ids that exist (they need not be 0..n_sm-1); reserve the highest `reserve_sms` of them
         unsigned int* d_seen = nullptr;
@@ -216,21 +252,22 @@ void b2_destroy(b2_ctx* ctx) {
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < B2_EPOCH_SLOTS; i++) {
         vslot& V = ctx->slot[i];
-        dbuf* vb[] = {&V.haff, &V.hflag, &V.pkjac, &V.pkst, &V.saff, &V.sflag, &V.f, &V.sumjac};
+        dbuf* vb[] = {&V.haff, &V.hflag, &V.pkjac, &V.pkst, &V.saff, &V.sflag, &V.f, &V.sumjac, &V.pkjac_r, &V.rscal, &V.sg_aff, &V.sg_flag, &V.f_g, &V.gpass};
         for (dbuf* b : vb)
             if (b->p) cudaFree(b->p);
-        cudaEvent_t evs[4] = {V.ev_join0, V.ev_join1, V.ev_seg, V.ev_tail_done};
+        cudaEvent_t evs[5] = {V.ev_join0, V.ev_join1, V.ev_seg, V.ev_tail_done, V.ev_fork};
         for (cudaEvent_t ev : evs)
             if (ev) cudaEventDestroy(ev);
         if (V.s_tail) cudaStreamDestroy(V.s_tail);
+        for (int k = 0; k < 2; k++)
+            if (V.s_aux[k]) cudaStreamDestroy(V.s_aux[k]);
     }
-    for (int i = 0; i < 2; i++)
-        if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->ev_lmd_done) cudaEventDestroy(ctx->ev_lmd_done);
     if (ctx->d_dec_counter) cudaFree(ctx->d_dec_counter);
+    if (ctx->d_guard) cudaFree(ctx->d_guard);
+    if (ctx->d_rlc_seed) cudaFree(ctx->d_rlc_seed);
     if (ctx->ev_votes_done) cudaEventDestroy(ctx->ev_votes_done);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
 
@@ -238,14 +275,28 @@ const char* b2_last_error(b2_ctx* ctx) { return ctx ? ctx->err : "null context";
 uint64_t b2_launch_count(b2_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint32_t b2_tree_size(b2_ctx* ctx) { return ctx ? ctx->n_blocks : 0; }
 int b2_sync(b2_ctx* ctx) {
+    B2_NVTX;
     REQUIRE(ctx, "null context");
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
     return B2_OK;
 }
 
+int b2_guard_flags(b2_ctx* ctx, uint32_t* flags_out) {
+    B2_NVTX;
+    REQUIRE(ctx && flags_out, "guard_flags: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    uint32_t f = 0;
+    CK(cudaMemcpy(&f, ctx->d_guard, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(ctx->d_guard, 0, 4));
+    *flags_out = f;
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------------------------------ registry
 int b2_registry_load(b2_ctx* ctx, const uint8_t* pk48, const uint64_t* eff, const uint8_t* flags, uint64_t n, uint8_t* pk_valid_out) {
+    B2_NVTX;
     REQUIRE(ctx && pk48 && eff && flags && n > 0 && n < (1ull << 32), "registry_load: bad arguments");
     CK(cudaSetDevice(ctx->device));
     int rc;
@@ -279,6 +330,7 @@ int b2_registry_load(b2_ctx* ctx, const uint8_t* pk48, const uint64_t* eff, cons
 }
 
 int b2_registry_update_balances(b2_ctx* ctx, const uint64_t* eff, const uint8_t* flags, uint64_t n) {
+    B2_NVTX;
     REQUIRE(ctx && eff && flags && n == ctx->n_val && n > 0, "registry_update_balances: registry not loaded or size mismatch");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->d_eff, eff, n * 8, cudaMemcpyHostToDevice, ctx->s_main));
@@ -313,18 +365,31 @@ static int upload_batch(b2_ctx* ctx, const uint32_t* members, const uint32_t* of
     return B2_OK;
 }
 
-static int g1_aggregate_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
-                            uint32_t n_agg, cudaStream_t s) {
-    int rc;
-    if ((rc = ensure(ctx, ctx->sc_pkjac, (size_t)n_agg * 144)) || (rc = ensure(ctx, ctx->sc_pkst, n_agg))) return rc;
-    k_g1_aggregate<<<n_agg, 128, 0, s>>>(ctx->d_records, ctx->d_valid, d_members, d_off, d_bits, bits_stride, n_agg,
-                                         (uint32_t*)ctx->sc_pkjac.p, (uint8_t*)ctx->sc_pkst.p);
+// K2 launch: one warp per aggregate through the TMA-staged gather (wpb warps = aggregates per block), or the LDG form with
+// `ldg_block` threads per aggregate
+static int launch_k2(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride, uint32_t n_agg,
+                     uint32_t* d_pkjac, uint8_t* d_pkst, unsigned wpb, unsigned ldg_block, cudaStream_t s) {
+    if (ctx->k2_tma) {
+        k_g1_gather_tma<false><<<blocks_for(n_agg, wpb), wpb * 32, wpb * sizeof(gather_ws), s>>>(ctx->d_records, d_members, d_off, d_bits, bits_stride, n_agg,
+                                                                                             d_pkjac, d_pkst, ctx->n_val, ctx->d_guard, nullptr);
+    } else {
+        k_g1_aggregate<<<n_agg, ldg_block, 0, s>>>(ctx->d_records, ctx->d_valid, d_members, d_off, d_bits, bits_stride, n_agg, d_pkjac, d_pkst, ctx->n_val,
+                                                   ctx->d_guard);
+    }
     CKL(ctx);
     return B2_OK;
 }
 
+static int g1_aggregate_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
+                            uint32_t n_agg, cudaStream_t s) {
+    int rc;
+    if ((rc = ensure(ctx, ctx->sc_pkjac, (size_t)n_agg * 144)) || (rc = ensure(ctx, ctx->sc_pkst, n_agg))) return rc;
+    return launch_k2(ctx, d_members, d_off, d_bits, bits_stride, n_agg, (uint32_t*)ctx->sc_pkjac.p, (uint8_t*)ctx->sc_pkst.p, 4, 128, s);
+}
+
 int b2_g1_aggregate(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride, uint32_t n_agg,
                     uint8_t* out48, uint8_t* status) {
+    B2_NVTX;
     REQUIRE(ctx && members && off && bits && out48 && status && n_agg > 0 && bits_stride > 0, "g1_aggregate: bad arguments");
     REQUIRE(ctx->n_val > 0, "g1_aggregate: registry not loaded");
     int rc;
@@ -343,6 +408,25 @@ int b2_g1_aggregate(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, c
     CK(cudaStreamSynchronize(s));
     memcpy(out48, t48.data(), t48.size());
     memcpy(status, tst.data(), n_agg);
+    return B2_OK;
+}
+
+// The gather stage of K2 ALONE (no additions): XOR checksum of the records each aggregate selects.  form 1: TMA-staged
+// (k_g1_gather_tma<true>), form 0: plain 128-bit loads (k_g1_gather_ldg_probe).  bench.py times it for `roofline.gather`.
+int b2_gather_probe_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride, uint32_t n_agg,
+                        int form, uint32_t* d_checksum_out, void* stream) {
+    B2_NVTX;
+    REQUIRE(ctx && d_members && d_off && d_bits && d_checksum_out && n_agg > 0 && bits_stride > 0 && (form == 0 || form == 1), "gather_probe_dev: bad arguments");
+    REQUIRE(ctx->n_val > 0, "gather_probe: registry not loaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (form == 1) {
+        k_g1_gather_tma<true><<<blocks_for(n_agg, 4), 128, 4 * sizeof(gather_ws), s>>>(ctx->d_records, d_members, d_off, d_bits, bits_stride, n_agg, nullptr,
+                                                                                    nullptr, ctx->n_val, ctx->d_guard, d_checksum_out);
+    } else {
+        k_g1_gather_ldg_probe<<<blocks_for(n_agg, 4), 128, 0, s>>>(ctx->d_records, d_members, d_off, d_bits, bits_stride, n_agg, ctx->n_val, d_checksum_out);
+    }
+    CKL(ctx);
     return B2_OK;
 }
 
@@ -365,7 +449,7 @@ static int aggregate_front(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, const 
         CKL(ctx);
     }
     k_g2_segment_sum<<<n_seg, 32, 0, s>>>((const uint32_t*)ctx->sc_g2aff.p, (const uint8_t*)ctx->sc_g2st.p, d_seg_off, n_seg,
-                                           (uint32_t*)V.sumjac.p, d_seg_status);
+                                           (uint32_t*)V.sumjac.p, d_seg_status, n_sig, ctx->d_guard);
     CKL(ctx);
     return B2_OK;
 }
@@ -381,6 +465,7 @@ static int aggregate_finish(b2_ctx* ctx, vslot& V, uint32_t n_seg, uint8_t* d_ou
 
 int b2_aggregate_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig, uint8_t* d_out96,
                      int32_t* d_seg_status, void* stream) {
+    B2_NVTX;
     REQUIRE(ctx && d_seg_off && d_out96 && d_seg_status && n_seg > 0 && (n_sig == 0 || d_sig96), "aggregate_dev: bad arguments");
     CK(cudaSetDevice(ctx->device));
     int rc;
@@ -389,6 +474,7 @@ int b2_aggregate_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_seg_
 }
 
 int b2_aggregate(b2_ctx* ctx, const uint8_t* sig96, const uint32_t* seg_off, uint32_t n_seg, uint8_t* out96, int32_t* seg_status) {
+    B2_NVTX;
     REQUIRE(ctx && seg_off && out96 && seg_status && n_seg > 0, "aggregate: bad arguments");
     REQUIRE(seg_off[0] == 0, "aggregate: seg_off[0] must be 0");
     for (uint32_t s = 0; s < n_seg; s++) REQUIRE(seg_off[s + 1] >= seg_off[s], "aggregate: seg_off must be non-decreasing");
@@ -466,32 +552,71 @@ static int verify_fork(b2_ctx* ctx, vslot& V, const pk_source& P, const uint8_t*
         (rc = ensure(ctx, V.pkst, n_agg)))
         return rc;
     if (P.d_pk48 && ((rc = ensure(ctx, ctx->sc_rec, P.n_pk * 96 + 16)) || (rc = ensure(ctx, ctx->sc_val, P.n_pk + 16)))) return rc;
-    CK(cudaEventRecord(ctx->ev_fork, s));
-    CK(cudaStreamWaitEvent(ctx->s_aux[0], ctx->ev_fork, 0));
-    CK(cudaStreamWaitEvent(ctx->s_aux[1], ctx->ev_fork, 0));
+    CK(cudaEventRecord(V.ev_fork, s));
+    CK(cudaStreamWaitEvent(V.s_aux[0], V.ev_fork, 0));
+    CK(cudaStreamWaitEvent(V.s_aux[1], V.ev_fork, 0));
     const unsigned tb = team ? 32u : ctx->tail_block;
-    k_hash_to_g2<<<blocks_for(n_agg, tb), tb, 0, ctx->s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)V.haff.p, (uint8_t*)V.hflag.p);
+    k_hash_to_g2<<<blocks_for(n_agg, tb), tb, 0, V.s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)V.haff.p, (uint8_t*)V.hflag.p);
     CKL(ctx);
-    CK(cudaEventRecord(V.ev_join0, ctx->s_aux[0]));
+    CK(cudaEventRecord(V.ev_join0, V.s_aux[0]));
     if (P.d_pk48) {
         if (P.n_pk) {
-            k_g1_decompress_validate<<<blocks_for(P.n_pk, 128), 128, 0, ctx->s_aux[1]>>>(P.d_pk48, P.n_pk, (uint32_t*)ctx->sc_rec.p, (uint8_t*)ctx->sc_val.p);
+            k_g1_decompress_validate<<<blocks_for(P.n_pk, 128), 128, 0, V.s_aux[1]>>>(P.d_pk48, P.n_pk, (uint32_t*)ctx->sc_rec.p, (uint8_t*)ctx->sc_val.p);
             CKL(ctx);
         }
-        k_g1_segment_sum<<<n_agg, 128, 0, ctx->s_aux[1]>>>((const uint32_t*)ctx->sc_rec.p, (const uint8_t*)ctx->sc_val.p, P.d_off, n_agg,
+        k_g1_segment_sum<<<n_agg, 128, 0, V.s_aux[1]>>>((const uint32_t*)ctx->sc_rec.p, (const uint8_t*)ctx->sc_val.p, P.d_off, n_agg,
                                                           (uint32_t*)V.pkjac.p, (uint8_t*)V.pkst.p);
         CKL(ctx);
     } else {
         // one block per aggregate.  128 threads when the caller waits; ONE WARP under the epoch pipeline: the 5-round shuffle tree costs
         // every warp 80 Fp multiplications whatever its share of the 512 records, so 4 warps spend 2.1x the multiply-pipe time of one
         const unsigned k2_block = team ? 128u : ctx->k2_block;
-        k_g1_aggregate<<<n_agg, k2_block, 0, ctx->s_aux[1]>>>(ctx->d_records, ctx->d_valid, P.d_members, P.d_off, P.d_bits, P.bits_stride, n_agg,
-                                                             (uint32_t*)V.pkjac.p, (uint8_t*)V.pkst.p);
-        CKL(ctx);
+        if ((rc = launch_k2(ctx, P.d_members, P.d_off, P.d_bits, P.bits_stride, n_agg, (uint32_t*)V.pkjac.p, (uint8_t*)V.pkst.p, team ? 4u : 1u, k2_block,
+                            V.s_aux[1])))
+            return rc;
     }
-    CK(cudaStreamWaitEvent(ctx->s_aux[1], V.ev_join0, 0));
-    if ((rc = launch_miller(ctx, V, n_agg, 1, team, ctx->s_aux[1]))) return rc;
-    CK(cudaEventRecord(V.ev_join1, ctx->s_aux[1]));
+    if (ctx->verify_mode == 1) {
+        // RLC: the pubkey-side Miller loop runs on [r_i] PK_i (thread-per-aggregate kernels: this mode trades latency for work)
+        const uint32_t n_groups = blocks_for(n_agg, B2_RLC_GROUP);
+        if ((rc = ensure(ctx, V.pkjac_r, (size_t)n_agg * 144)) || (rc = ensure(ctx, V.rscal, (size_t)n_agg * 8)) || (rc = ensure(ctx, V.sg_aff, (size_t)n_groups * 192)) ||
+            (rc = ensure(ctx, V.sg_flag, n_groups)) || (rc = ensure(ctx, V.f_g, (size_t)n_groups * 2 * 576)) || (rc = ensure(ctx, V.gpass, n_groups)))
+            return rc;
+        k_rlc_pk<<<blocks_for(n_agg, ctx->tail_block), ctx->tail_block, 0, V.s_aux[1]>>>(ctx->d_rlc_seed, d_msg32, (const uint32_t*)V.pkjac.p, (const uint8_t*)V.pkst.p,
+                                                                                        n_agg, (unsigned long long*)V.rscal.p, (uint32_t*)V.pkjac_r.p);
+        CKL(ctx);
+        CK(cudaStreamWaitEvent(V.s_aux[1], V.ev_join0, 0));
+        k_miller<<<blocks_for(n_agg, ctx->tail_block), ctx->tail_block, 0, V.s_aux[1]>>>((const uint32_t*)V.pkjac_r.p, (const uint8_t*)V.pkst.p, (const uint32_t*)V.haff.p,
+                                                                                        (const uint8_t*)V.hflag.p, nullptr, nullptr, n_agg, (uint32_t*)V.f.p, 1);
+        CKL(ctx);
+        CK(cudaEventRecord(V.ev_join1, V.s_aux[1]));
+        return B2_OK;
+    }
+    CK(cudaStreamWaitEvent(V.s_aux[1], V.ev_join0, 0));
+    if ((rc = launch_miller(ctx, V, n_agg, 1, team, V.s_aux[1]))) return rc;
+    CK(cudaEventRecord(V.ev_join1, V.s_aux[1]));
+    return B2_OK;
+}
+// RLC batch mode, signature half + verdicts (V.saff / V.sflag hold the affine, subgroup-checked aggregate signatures)
+static int verify_main_rlc(b2_ctx* ctx, vslot& V, uint32_t n_agg, uint8_t* d_ok, cudaStream_t s) {
+    const uint32_t n_groups = blocks_for(n_agg, B2_RLC_GROUP);
+    const unsigned tb = ctx->tail_block;
+    const uint8_t *pkst = (const uint8_t*)V.pkst.p, *sflag = (const uint8_t*)V.sflag.p;
+    k_rlc_sig<<<n_groups, 32, 0, s>>>((const uint32_t*)V.saff.p, sflag, pkst, (const unsigned long long*)V.rscal.p, n_agg, (uint32_t*)V.sg_aff.p, (uint8_t*)V.sg_flag.p);
+    CKL(ctx);
+    // e(-g1, sum [r_i] S_i) per group
+    k_miller<<<blocks_for(n_groups, tb), tb, 0, s>>>(nullptr, nullptr, nullptr, nullptr, (const uint32_t*)V.sg_aff.p, (const uint8_t*)V.sg_flag.p, n_groups, (uint32_t*)V.f_g.p, 2);
+    CKL(ctx);
+    CK(cudaStreamWaitEvent(s, V.ev_join1, 0));
+    k_rlc_final<<<blocks_for(n_groups, 32), 32, 0, s>>>((const uint32_t*)V.f.p, (const uint32_t*)V.f_g.p, pkst, sflag, n_agg, n_groups, (uint8_t*)V.gpass.p);
+    CKL(ctx);
+    k_rlc_verdict<<<blocks_for(n_agg, 128), 128, 0, s>>>(pkst, sflag, (const uint8_t*)V.gpass.p, n_agg, d_ok);
+    CKL(ctx);
+    // fallback: the members of a failed group, aggregate by aggregate (threads of passed groups exit at once)
+    k_miller<<<blocks_for(2 * n_agg, tb), tb, 0, s>>>((const uint32_t*)V.pkjac.p, pkst, (const uint32_t*)V.haff.p, (const uint8_t*)V.hflag.p, (const uint32_t*)V.saff.p, sflag,
+                                                       n_agg, (uint32_t*)V.f.p, 0, (const uint8_t*)V.gpass.p, B2_RLC_GROUP);
+    CKL(ctx);
+    k_final_verdict<<<blocks_for(n_agg, tb), tb, 0, s>>>((const uint32_t*)V.f.p, pkst, sflag, n_agg, d_ok, (const uint8_t*)V.gpass.p, B2_RLC_GROUP);
+    CKL(ctx);
     return B2_OK;
 }
 // d_sig96 == nullptr: the signature points are already in V.saff / V.sflag (handed over by aggregate_finish)
@@ -501,6 +626,7 @@ static int verify_main(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, uint32_t n
         k_sig_prepare<<<blocks_for(n_agg, 32), 32, 0, s>>>(d_sig96, n_agg, (uint32_t*)V.saff.p, (uint8_t*)V.sflag.p);
         CKL(ctx);
     }
+    if (ctx->verify_mode == 1) return verify_main_rlc(ctx, V, n_agg, d_ok, s);
     if ((rc = launch_miller(ctx, V, n_agg, 2, team, s))) return rc;
     CK(cudaStreamWaitEvent(s, V.ev_join1, 0));
     return launch_final(ctx, V, n_agg, d_ok, team, s);
@@ -508,6 +634,7 @@ static int verify_main(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, uint32_t n
 
 int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
                                  const uint8_t* d_msg32, const uint8_t* d_sig96, uint32_t n_agg, uint8_t* d_ok_out, void* stream) {
+    B2_NVTX;
     REQUIRE(ctx && d_members && d_off && d_bits && d_msg32 && d_sig96 && d_ok_out && n_agg > 0 && bits_stride > 0, "fast_aggregate_verify_dev: bad arguments");
     REQUIRE(ctx->n_val > 0, "fast_aggregate_verify: registry not loaded");
     CK(cudaSetDevice(ctx->device));
@@ -544,10 +671,12 @@ static int epoch_tail(b2_ctx* ctx, int slot, const uint32_t* d_members, const ui
     CK(cudaStreamWaitEvent(t, V.ev_seg, 0));
     if ((rc = aggregate_finish(ctx, V, n_agg, d_agg_sig96, d_agg_status, true, t, team ? 32u : ctx->tail_block))) return rc;
     if ((rc = verify_main(ctx, V, nullptr, n_agg, d_ok_out, t, team))) return rc;
-    CK(cudaStreamWaitEvent(t, ctx->ev_votes_done, 0));  // do not move the LMD table under a vote scatter that is still reading it
-    CK(cudaStreamWaitEvent(t, ctx->ev_lmd_done, 0));    // latest messages are applied in epoch order even when tails overlap
-    if ((rc = b2_latest_messages_update_dev(ctx, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_ok_out, n_agg, t))) return rc;
-    CK(cudaEventRecord(ctx->ev_lmd_done, t));
+    if (d_target_epoch) {
+        CK(cudaStreamWaitEvent(t, ctx->ev_votes_done, 0));  // do not move the LMD table under a vote scatter that is still reading it
+        CK(cudaStreamWaitEvent(t, ctx->ev_lmd_done, 0));    // latest messages are applied in epoch order even when tails overlap
+        if ((rc = b2_latest_messages_update_dev(ctx, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_ok_out, n_agg, t))) return rc;
+        CK(cudaEventRecord(ctx->ev_lmd_done, t));
+    }   // else: the caller applies update_latest_messages itself, after exchanging the verdicts of all ranks (sharded epoch)
     CK(cudaEventRecord(V.ev_tail_done, t));
     return B2_OK;
 }
@@ -555,7 +684,8 @@ static int epoch_tail(b2_ctx* ctx, int slot, const uint32_t* d_members, const ui
 int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                  uint32_t bits_stride, const uint8_t* d_msg32, const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg,
                  uint64_t n_sig, uint8_t* d_agg_sig96, int32_t* d_agg_status, uint8_t* d_ok_out, void* stream) {
-    REQUIRE(ctx && d_sig96 && d_members && d_off && d_bits && d_msg32 && d_target_epoch && d_block_idx && d_agg_sig96 && d_agg_status && d_ok_out &&
+    B2_NVTX;
+    REQUIRE(ctx && d_sig96 && d_members && d_off && d_bits && d_msg32 && (!d_target_epoch == !d_block_idx) && d_agg_sig96 && d_agg_status && d_ok_out &&
                 n_agg > 0 && bits_stride > 0, "epoch_dev: bad arguments");
     REQUIRE(ctx->n_val > 0, "epoch_dev: registry not loaded");
     CK(cudaSetDevice(ctx->device));
@@ -570,6 +700,7 @@ int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members,
 // consecutive epochs overlap each other and the following decompressions; latest messages are still applied in epoch order.
 int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                        uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, void* stream) {
+    B2_NVTX;
     REQUIRE(ctx && slot >= 0 && slot < B2_EPOCH_SLOTS && d_sig96 && d_members && d_off && d_bits && d_msg32 && d_agg_status && n_agg > 0 && bits_stride > 0,
             "epoch_start_dev: bad arguments");
     REQUIRE(ctx->n_val > 0, "epoch_start_dev: registry not loaded");
@@ -580,18 +711,21 @@ int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint
 int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
                       const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
                       uint8_t* d_ok_out) {
-    REQUIRE(ctx && slot >= 0 && slot < B2_EPOCH_SLOTS && d_members && d_off && d_bits && d_target_epoch && d_block_idx && d_agg_sig96 && d_agg_status && d_ok_out &&
+    B2_NVTX;
+    REQUIRE(ctx && slot >= 0 && slot < B2_EPOCH_SLOTS && d_members && d_off && d_bits && (!d_target_epoch == !d_block_idx) && d_agg_sig96 && d_agg_status && d_ok_out &&
                 n_agg > 0 && bits_stride > 0, "epoch_tail_dev: bad arguments");
     CK(cudaSetDevice(ctx->device));
     return epoch_tail(ctx, slot, d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, n_agg, d_agg_sig96, d_agg_status, d_ok_out,
                       ctx->slot[slot].s_tail, ctx->epoch_team);
 }
 int b2_epoch_set_pairing_form(b2_ctx* ctx, int form) {
+    B2_NVTX;
     REQUIRE(ctx && (form == 0 || form == 1), "epoch_set_pairing_form: bad arguments");
     ctx->epoch_team = form == 1;
     return B2_OK;
 }
 int b2_epoch_wait_dev(b2_ctx* ctx, int slot, void* stream) {
+    B2_NVTX;
     REQUIRE(ctx && slot >= 0 && slot < B2_EPOCH_SLOTS, "epoch_wait_dev: bad arguments");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->slot[slot].ev_tail_done, 0));
@@ -600,6 +734,7 @@ int b2_epoch_wait_dev(b2_ctx* ctx, int slot, void* stream) {
 
 int b2_fast_aggregate_verify(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
                              const uint8_t* msg32, const uint8_t* sig96, uint32_t n_agg, uint8_t* ok_out) {
+    B2_NVTX;
     REQUIRE(ctx && members && off && bits && msg32 && sig96 && ok_out && n_agg > 0 && bits_stride > 0, "fast_aggregate_verify: bad arguments");
     REQUIRE(ctx->n_val > 0, "fast_aggregate_verify: registry not loaded");
     int rc;
@@ -623,6 +758,7 @@ int b2_fast_aggregate_verify(b2_ctx* ctx, const uint32_t* members, const uint32_
 
 int b2_fast_aggregate_verify_pks(b2_ctx* ctx, const uint8_t* pk48, const uint32_t* pk_off, const uint8_t* msg32, const uint8_t* sig96,
                                  uint32_t n_agg, uint8_t* ok_out) {
+    B2_NVTX;
     REQUIRE(ctx && pk_off && msg32 && sig96 && ok_out && n_agg > 0, "fast_aggregate_verify_pks: bad arguments");
     REQUIRE(pk_off[0] == 0, "pk_off[0] must be 0");
     for (uint32_t a = 0; a < n_agg; a++) REQUIRE(pk_off[a + 1] >= pk_off[a], "pk_off must be non-decreasing");
@@ -652,6 +788,7 @@ int b2_fast_aggregate_verify_pks(b2_ctx* ctx, const uint8_t* pk48, const uint32_
 
 // ------------------------------------------------------------------------------------------ SkToPk / Sign / hash_to_g2
 int b2_sk_to_pk(b2_ctx* ctx, const uint32_t* sk8, uint64_t n, uint8_t* pk48_out) {
+    B2_NVTX;
     REQUIRE(ctx && sk8 && pk48_out && n > 0, "sk_to_pk: bad arguments");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->s_main;
@@ -666,6 +803,7 @@ int b2_sk_to_pk(b2_ctx* ctx, const uint32_t* sk8, uint64_t n, uint8_t* pk48_out)
 }
 
 int b2_hash_to_g2(b2_ctx* ctx, const uint8_t* msg32, uint32_t n_msg, uint8_t* out96) {
+    B2_NVTX;
     REQUIRE(ctx && msg32 && out96 && n_msg > 0, "hash_to_g2: bad arguments");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->s_main;
@@ -684,6 +822,7 @@ int b2_hash_to_g2(b2_ctx* ctx, const uint8_t* msg32, uint32_t n_msg, uint8_t* ou
 }
 
 int b2_sign(b2_ctx* ctx, const uint32_t* sk8, const uint32_t* msg_idx, uint64_t n, const uint8_t* msg32, uint32_t n_msg, uint8_t* sig96_out) {
+    B2_NVTX;
     REQUIRE(ctx && sk8 && msg_idx && msg32 && sig96_out && n > 0 && n_msg > 0, "sign: bad arguments");
     for (uint64_t i = 0; i < n; i++) REQUIRE(msg_idx[i] < n_msg, "sign: msg_idx out of range");
     CK(cudaSetDevice(ctx->device));
@@ -706,6 +845,7 @@ int b2_sign(b2_ctx* ctx, const uint32_t* sk8, const uint32_t* msg_idx, uint64_t 
 
 // ------------------------------------------------------------------------------------------ batched SHA-256
 int b2_sha256_batch(b2_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint64_t n, uint8_t* out32) {
+    B2_NVTX;
     REQUIRE(ctx && out32 && n > 0 && (msg_len == 0 || msgs), "sha256_batch: bad arguments");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->s_main;
@@ -721,6 +861,7 @@ int b2_sha256_batch(b2_ctx* ctx, const uint8_t* msgs, uint32_t msg_len, uint64_t
 
 // ------------------------------------------------------------------------------------------ SSZ signing roots
 int b2_signing_roots(b2_ctx* ctx, const uint8_t* data128, const uint8_t* domain32, int per_attestation_domain, uint32_t n, uint8_t* out32) {
+    B2_NVTX;
     REQUIRE(ctx && data128 && domain32 && out32 && n > 0, "signing_roots: bad arguments");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->s_main;
@@ -740,6 +881,7 @@ int b2_signing_roots(b2_ctx* ctx, const uint8_t* data128, const uint8_t* domain3
 // ------------------------------------------------------------------------------------------ SSZ wire decode (:714-717)
 int b2_attestations_decode(b2_ctx* ctx, const uint8_t* wire, const uint32_t* woff, uint32_t n, uint32_t bits_stride, uint32_t max_bits,
                            uint8_t* bits_out, uint32_t* bit_len_out, uint8_t* data128_out, uint8_t* sig96_out, int32_t* status_out) {
+    B2_NVTX;
     REQUIRE(ctx && wire && woff && n > 0 && bits_stride > 0 && bits_out && bit_len_out && data128_out && sig96_out && status_out,
             "attestations_decode: bad arguments");
     REQUIRE(woff[0] == 0, "attestations_decode: woff[0] must be 0");
@@ -771,6 +913,7 @@ int b2_attestations_decode(b2_ctx* ctx, const uint8_t* wire, const uint32_t* wof
 // ------------------------------------------------------------------------------------------ committee shuffle
 int b2_shuffle_committees_dev(b2_ctx* ctx, const uint8_t* d_seed32, const uint32_t* d_active, uint32_t n_active, uint32_t rounds,
                               uint32_t* d_members_out, void* stream) {
+    B2_NVTX;
     REQUIRE(ctx && d_seed32 && d_members_out && rounds <= 255, "shuffle_committees_dev: bad arguments");
     if (n_active == 0) return B2_OK;
     CK(cudaSetDevice(ctx->device));
@@ -790,6 +933,7 @@ int b2_shuffle_committees_dev(b2_ctx* ctx, const uint8_t* d_seed32, const uint32
 }
 
 int b2_shuffle_committees(b2_ctx* ctx, const uint8_t* seed32, const uint32_t* active, uint32_t n_active, uint32_t rounds, uint32_t* members_out) {
+    B2_NVTX;
     REQUIRE(ctx && seed32 && members_out && rounds <= 255, "shuffle_committees: bad arguments");
     if (n_active == 0) return B2_OK;
     CK(cudaSetDevice(ctx->device));
@@ -809,6 +953,7 @@ int b2_shuffle_committees(b2_ctx* ctx, const uint8_t* seed32, const uint32_t* ac
 
 // ------------------------------------------------------------------------------------------ latest messages
 int b2_latest_messages_reset(b2_ctx* ctx) {
+    B2_NVTX;
     REQUIRE(ctx && ctx->n_val > 0, "latest_messages_reset: registry not loaded");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_lmd_key, 0, ctx->n_val * 8, ctx->s_main));
@@ -820,6 +965,7 @@ int b2_latest_messages_reset(b2_ctx* ctx) {
 
 int b2_latest_messages_load(b2_ctx* ctx, const uint64_t* epoch, const uint32_t* block_idx, const uint8_t* has_msg, const uint8_t* equivocating,
                             uint64_t n) {
+    B2_NVTX;
     REQUIRE(ctx && epoch && block_idx && has_msg && equivocating && n == ctx->n_val && n > 0, "latest_messages_load: bad arguments / registry size");
     std::vector<unsigned long long> key(n);
     for (uint64_t v = 0; v < n; v++) {
@@ -836,6 +982,7 @@ int b2_latest_messages_load(b2_ctx* ctx, const uint64_t* epoch, const uint32_t* 
 }
 
 int b2_latest_messages_read(b2_ctx* ctx, uint64_t* epoch, uint32_t* block_idx, uint8_t* has_msg, uint64_t n) {
+    B2_NVTX;
     REQUIRE(ctx && epoch && block_idx && has_msg && n == ctx->n_val && n > 0, "latest_messages_read: bad arguments / registry size");
     std::vector<unsigned long long> key(n);
     CK(cudaSetDevice(ctx->device));
@@ -853,20 +1000,23 @@ int b2_latest_messages_read(b2_ctx* ctx, uint64_t* epoch, uint32_t* block_idx, u
 
 int b2_latest_messages_update_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
                                   const uint64_t* d_target_epoch, const uint32_t* d_block_idx, const uint8_t* d_accept, uint32_t n_agg, void* stream) {
+    B2_NVTX;
     REQUIRE(ctx && d_members && d_off && d_bits && d_target_epoch && d_block_idx && n_agg > 0 && bits_stride > 0, "latest_messages_update_dev: bad arguments");
     REQUIRE(ctx->n_val > 0, "latest_messages_update: registry not loaded");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
-    k_lmd_phase1<<<n_agg, 128, 0, s>>>(d_members, d_off, d_bits, bits_stride, d_target_epoch, d_accept, ctx->d_equiv, n_agg, ctx->d_lmd_key);
+    k_lmd_phase1<<<n_agg, 128, 0, s>>>(d_members, d_off, d_bits, bits_stride, d_target_epoch, d_accept, ctx->d_equiv, n_agg, ctx->d_lmd_key,
+                                       ctx->n_val, ctx->d_guard);
     CKL(ctx);
     k_lmd_phase2<<<n_agg, 128, 0, s>>>(d_members, d_off, d_bits, bits_stride, d_target_epoch, d_block_idx, d_accept, ctx->d_equiv, n_agg,
-                                       ctx->d_lmd_key, ctx->d_lmd_block);
+                                       ctx->d_lmd_key, ctx->d_lmd_block, ctx->n_val);
     CKL(ctx);
     return B2_OK;
 }
 
 int b2_latest_messages_update(b2_ctx* ctx, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
                               const uint64_t* target_epoch, const uint32_t* block_idx, const uint8_t* accept, uint32_t n_agg) {
+    B2_NVTX;
     REQUIRE(ctx && members && off && bits && target_epoch && block_idx && n_agg > 0 && bits_stride > 0, "latest_messages_update: bad arguments");
     REQUIRE(ctx->n_val > 0, "latest_messages_update: registry not loaded");
     int rc;
@@ -890,6 +1040,7 @@ int b2_latest_messages_update(b2_ctx* ctx, const uint32_t* members, const uint32
 
 // ------------------------------------------------------------------------------------------ participation flags (process_attestation :738-754)
 int b2_participation_load(b2_ctx* ctx, int which, const uint8_t* participation, uint64_t n) {
+    B2_NVTX;
     REQUIRE(ctx && (which == 0 || which == 1) && participation && n == ctx->n_val && n > 0, "participation_load: bad arguments / registry size");
     CK(cudaSetDevice(ctx->device));
     int rc;
@@ -905,6 +1056,7 @@ int b2_participation_load(b2_ctx* ctx, int which, const uint8_t* participation, 
     return B2_OK;
 }
 int b2_participation_read(b2_ctx* ctx, int which, uint8_t* participation_out, uint64_t n) {
+    B2_NVTX;
     REQUIRE(ctx && (which == 0 || which == 1) && participation_out && n == ctx->n_val && ctx->d_part[which], "participation_read: not loaded / bad arguments");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(participation_out, ctx->d_part[which], n, cudaMemcpyDeviceToHost, ctx->s_main));
@@ -914,6 +1066,7 @@ int b2_participation_read(b2_ctx* ctx, int which, uint8_t* participation_out, ui
 int b2_participation_update(b2_ctx* ctx, int which, const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t bits_stride,
                             const uint8_t* flag_mask, const uint8_t* accept, uint32_t n_agg, uint64_t effective_balance_increment,
                             uint64_t base_reward_per_increment, uint64_t* numerator_out) {
+    B2_NVTX;
     REQUIRE(ctx && (which == 0 || which == 1) && members && off && bits && flag_mask && numerator_out && n_agg > 0 && bits_stride > 0 &&
                 effective_balance_increment > 0, "participation_update: bad arguments");
     REQUIRE(ctx->n_val > 0 && ctx->d_part[which], "participation_update: registry / participation table not loaded");
@@ -941,6 +1094,7 @@ int b2_participation_update(b2_ctx* ctx, int which, const uint32_t* members, con
 
 // ------------------------------------------------------------------------------------------ FFG balance sums (:793-803)
 int b2_ffg_balances(b2_ctx* ctx, uint32_t flag_index, uint64_t* out4) {
+    B2_NVTX;
     REQUIRE(ctx && out4 && flag_index < 8, "ffg_balances: bad arguments");
     REQUIRE(ctx->n_val > 0, "ffg_balances: registry not loaded");
     CK(cudaSetDevice(ctx->device));
@@ -958,13 +1112,25 @@ int b2_ffg_balances(b2_ctx* ctx, uint32_t flag_index, uint64_t* out4) {
 
 // ------------------------------------------------------------------------------------------ fork-choice variants
 int b2_set_fork_choice_params(b2_ctx* ctx, uint64_t min_vote_epoch, int exclude_slashed) {
+    B2_NVTX;
     REQUIRE(ctx && min_vote_epoch < 0xffffffffull, "set_fork_choice_params: bad arguments");
     ctx->fc_min_key = (unsigned long long)min_vote_epoch << 32;
     ctx->fc_exclude_slashed = exclude_slashed ? 1 : 0;
     return B2_OK;
 }
 
+int b2_set_verify_mode(b2_ctx* ctx, int mode, const uint8_t* seed32) {
+    B2_NVTX;
+    REQUIRE(ctx && (mode == 0 || (mode == 1 && seed32)), "set_verify_mode: bad arguments (mode 1 needs a 32-byte seed)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());                   // no epoch in flight may see the mode change half way
+    if (mode == 1) CK(cudaMemcpy(ctx->d_rlc_seed, seed32, 32, cudaMemcpyHostToDevice));
+    ctx->verify_mode = mode;
+    return B2_OK;
+}
+
 int b2_on_attester_slashing(b2_ctx* ctx, const uint32_t* indices_1, uint32_t n1, const uint32_t* indices_2, uint32_t n2) {
+    B2_NVTX;
     REQUIRE(ctx && ctx->n_val > 0 && (n1 == 0 || indices_1) && (n2 == 0 || indices_2), "on_attester_slashing: bad arguments / registry not loaded");
     for (uint32_t i = 1; i < n1; i++) REQUIRE(indices_1[i - 1] < indices_1[i], "on_attester_slashing: attesting_indices must be sorted and unique");
     for (uint32_t i = 1; i < n2; i++) REQUIRE(indices_2[i - 1] < indices_2[i], "on_attester_slashing: attesting_indices must be sorted and unique");
@@ -983,6 +1149,7 @@ int b2_on_attester_slashing(b2_ctx* ctx, const uint32_t* indices_1, uint32_t n1,
 
 // ------------------------------------------------------------------------------------------ block tree
 int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, const uint8_t* root32, const uint8_t* leaf_viable, uint32_t n) {
+    B2_NVTX;
     REQUIRE(ctx && parent && slot && root32 && leaf_viable && n > 0, "tree_load: bad arguments");
     for (uint32_t b = 1; b < n; b++) REQUIRE(parent[b] < b, "tree_load: blocks must be in topological order (parent[b] < b)");
     // children in CSR form
@@ -1042,28 +1209,41 @@ int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, cons
     return B2_OK;
 }
 
-int b2_vote_weights_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, void* stream) {
+int b2_vote_weights_range_dev(b2_ctx* ctx, uint64_t v_begin, uint64_t v_end, uint64_t* d_votes_preorder, void* stream) {
+    B2_NVTX;
     REQUIRE(ctx && d_votes_preorder, "vote_weights_dev: bad arguments");
     REQUIRE(ctx->n_val > 0 && ctx->n_blocks > 0, "vote_weights: registry or tree not loaded");
+    REQUIRE(v_begin <= v_end && v_end <= ctx->n_val, "vote_weights_range: validator range outside the registry");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
+    const uint64_t n = v_end - v_begin;
     const size_t bins_bytes = (size_t)ctx->n_blocks * 8;
-    if (bins_bytes <= 200 * 1024) {
-        k_ghost_votes_smem<<<ctx->n_sm, 1024, bins_bytes, s>>>(ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff,
-                                                              ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder, ctx->fc_min_key, 1u,
-                                                              ctx->fc_exclude_slashed ? 3u : 1u);
+    if (n == 0) {
+        // nothing to scatter; the accumulator is clean by contract
+    } else if (bins_bytes <= 200 * 1024) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->n_sm, (n + 1023) / 1024);
+        k_ghost_votes_smem<<<grid, 1024, bins_bytes, s>>>(n, ctx->d_lmd_key + v_begin, ctx->d_lmd_block + v_begin, ctx->d_equiv + v_begin, ctx->d_flags + v_begin,
+                                                         ctx->d_eff + v_begin, ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder, ctx->fc_min_key, 1u,
+                                                         ctx->fc_exclude_slashed ? 3u : 1u);
+        CKL(ctx);
     } else {
-        k_ghost_votes<<<blocks_for(ctx->n_val, 256), 256, 0, s>>>(ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff,
-                                                                  ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder, ctx->fc_min_key, 1u,
-                                                              ctx->fc_exclude_slashed ? 3u : 1u);
+        k_ghost_votes<<<blocks_for(n, 256), 256, 0, s>>>(n, ctx->d_lmd_key + v_begin, ctx->d_lmd_block + v_begin, ctx->d_equiv + v_begin, ctx->d_flags + v_begin,
+                                                         ctx->d_eff + v_begin, ctx->d_pre, ctx->n_blocks, (unsigned long long*)d_votes_preorder, ctx->fc_min_key, 1u,
+                                                         ctx->fc_exclude_slashed ? 3u : 1u);
+        CKL(ctx);
     }
-    CKL(ctx);
     CK(cudaEventRecord(ctx->ev_votes_done, s));
     return B2_OK;
+}
+int b2_vote_weights_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, void* stream) {
+    B2_NVTX;
+    REQUIRE(ctx, "vote_weights_dev: bad arguments");
+    return b2_vote_weights_range_dev(ctx, 0, ctx->n_val, d_votes_preorder, stream);
 }
 
 int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
                            uint64_t* d_weight_out, uint32_t* d_head_idx_out, void* stream) {
+    B2_NVTX;
     REQUIRE(ctx && d_votes_preorder && d_head_idx_out, "head_from_votes_dev: bad arguments");
     REQUIRE(ctx->n_blocks > 0, "head_from_votes: tree not loaded");
     REQUIRE(justified_idx < ctx->n_blocks && boost_idx < (int32_t)ctx->n_blocks, "head_from_votes: block index out of range");
@@ -1093,6 +1273,7 @@ int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t jus
 }
 
 int b2_get_weights(b2_ctx* ctx, int32_t boost_idx, uint64_t boost_score, uint64_t* weight_out) {
+    B2_NVTX;
     REQUIRE(ctx && weight_out, "get_weights: bad arguments");
     REQUIRE(ctx->n_val > 0 && ctx->n_blocks > 0, "get_weights: registry or tree not loaded");
     int rc;
@@ -1105,6 +1286,7 @@ int b2_get_weights(b2_ctx* ctx, int32_t boost_idx, uint64_t boost_score, uint64_
 }
 
 int b2_get_head(b2_ctx* ctx, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score, uint32_t* head_idx_out) {
+    B2_NVTX;
     REQUIRE(ctx && head_idx_out, "get_head: bad arguments");
     REQUIRE(ctx->n_val > 0 && ctx->n_blocks > 0, "get_head: registry or tree not loaded");
     int rc;

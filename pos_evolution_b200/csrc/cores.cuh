@@ -15,7 +15,7 @@
 namespace b2 {
 
 // status bits of an aggregated pubkey (mirrors the ways py_ecc FastAggregateVerify returns False)
-enum PkStatus : uint32_t { PK_OK = 0, PK_INVALID_KEY = 1, PK_EMPTY = 2, PK_INFINITY = 4 };
+enum PkStatus : uint32_t { PK_OK = 0, PK_INVALID_KEY = 1, PK_EMPTY = 2, PK_INFINITY = 4, PK_BAD_INDEX = 8 /* member index outside the registry, or a malformed committee row */ };
 // signature flags
 enum SigFlag : uint8_t { SIG_OK = 0, SIG_INFINITY = 1, SIG_INVALID = 2 };
 
@@ -59,10 +59,14 @@ HD g1_aff load_record(const uint32_t* records, uint32_t idx) {
 // ---- K2: one member of one aggregate (bit j of aggregate a)
 HD void core_g1_accumulate(const uint32_t* records, const uint8_t* valid, const uint32_t* members, const uint32_t* off,
                            const uint8_t* bits, uint32_t bits_stride, uint32_t a, uint32_t j, g1_jac& acc, uint32_t& status,
-                           uint32_t& cnt) {
+                           uint32_t& cnt, uint64_t n_val = ~0ull) {
     if (!((bits[(uint64_t)a * bits_stride + (j >> 3)] >> (j & 7)) & 1)) return;
     uint32_t idx = members[off[a] + j];
     cnt++;
+    if (idx >= n_val) {                      // device-pointer entry points cannot be validated on the host: never read out of bounds
+        status |= PK_BAD_INDEX;
+        return;
+    }
     if (!valid[idx]) {
         status |= PK_INVALID_KEY;
         return;
@@ -157,6 +161,69 @@ HD fp12 core_miller_sig(const g2_aff& s, uint8_t sflag) {
 HD uint8_t core_final_verdict(const fp12& f0, const fp12& f1, uint8_t pk_status, uint8_t sflag) {
     if (pk_status != PK_OK || sflag == SIG_INVALID) return 0;
     return fp12_is_one(final_exponentiation(fp12_mul(f0, f1))) ? 1 : 0;
+}
+
+// ---- random-linear-combination batch verification (SURVEY.md section 8(f)-4, section 2 K6 "optional RLC batch mode")
+// Instead of n independent checks e(PK_i, H_i) * e(-g1, S_i) == 1, one check per group of aggregates:
+//     prod_i e([r_i] PK_i, H_i)  *  e(-g1, sum_i [r_i] S_i)  ==  1
+// with 64-bit scalars r_i the signer cannot predict (they are derived from a verifier-chosen secret seed): one Miller loop
+// and ONE final exponentiation per group instead of one of each per aggregate.  A group that fails is re-verified aggregate
+// by aggregate, so every verdict is the one the per-aggregate rule gives (a false accept needs a 2^-63 coincidence).
+HD uint64_t core_rlc_scalar(const uint8_t* seed32, uint32_t i, const uint8_t* msg32) {
+    uint8_t buf[68], out[32];
+#pragma unroll 1
+    for (int k = 0; k < 32; k++) {
+        buf[k] = seed32[k];
+        buf[36 + k] = msg32[k];
+    }
+    buf[32] = (uint8_t)i;
+    buf[33] = (uint8_t)(i >> 8);
+    buf[34] = (uint8_t)(i >> 16);
+    buf[35] = (uint8_t)(i >> 24);
+    sha256_ctx c;
+    sha256_init(c);
+    sha256_update(c, buf, 68);
+    sha256_final(c, out);
+    uint64_t r = 0;
+#pragma unroll 1
+    for (int k = 7; k >= 0; k--) r = (r << 8) | out[k];
+    return r | 1ull;                            // never zero
+}
+// [k]P for a per-thread 64-bit scalar: branch-free double-and-always-add
+template <class F> HDN jac<F> pt_mul_var64(const jac<F>& p, uint64_t k) {
+    jac<F> r = pt_inf<F>();
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        r = pt_dbl(r);
+        jac<F> s = pt_add(r, p);
+        r = pt_select(((k >> i) & 1ull) != 0, s, r);
+    }
+    return r;
+}
+template <class F> HDN jac<F> pt_mul_var64_aff(const aff<F>& p, uint64_t k) {
+    jac<F> r = pt_inf<F>();
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        r = pt_dbl(r);
+        jac<F> s = pt_add_mixed(r, p);
+        r = pt_select(((k >> i) & 1ull) != 0, s, r);
+    }
+    return r;
+}
+// is aggregate a part of its group's batch equation?  (a bad key set or an undecodable / non-G2 signature is rejected outright)
+HD bool rlc_in_batch(uint8_t pk_status, uint8_t sflag) { return pk_status == PK_OK && sflag != SIG_INVALID; }
+// group verdict: F = f_sig * prod f_pk[i] over the batch members; no member -> nothing to prove
+HD uint8_t core_rlc_group_verdict(const fp12& f_sig, const fp12* f_pk, const uint8_t* in_batch, uint32_t n) {
+    fp12 F = f_sig;
+    bool any = false;
+#pragma unroll 1
+    for (uint32_t i = 0; i < n; i++)
+        if (in_batch[i]) {
+            F = fp12_mul(F, f_pk[i]);
+            any = true;
+        }
+    if (!any) return 1;
+    return fp12_is_one(final_exponentiation(F)) ? 1 : 0;
 }
 
 // ---- SSZ: compute_signing_root(AttestationData, domain) (see k_signing_roots in kernels.cuh)

@@ -48,26 +48,49 @@ __global__ void __launch_bounds__(128) k_registry_load(const uint8_t* __restrict
     if (i < n) core_registry_load(pk48, records, valid, i);
 }
 
+// ------------------------------------------------------------------------------------------ device-side input guards
+// The *_dev entry points take device pointers, which the host cannot validate (b2_fast_aggregate_verify & co. do: check_batch).
+// Every kernel that follows caller-supplied indices therefore checks them itself: a committee row whose offsets run backwards or
+// whose size exceeds the bit row, a member index >= n_val, or a target epoch that does not fit the 32-bit key field is SKIPPED
+// (the aggregate then fails verification / contributes nothing) and recorded in the context's guard word (b2_guard_flags).
+enum GuardBits : uint32_t { GUARD_BAD_INDEX = 1, GUARD_BAD_ROW = 2, GUARD_BAD_EPOCH = 4 };
+__device__ __forceinline__ uint32_t guarded_row_size(const uint32_t* off, uint32_t a, uint32_t bits_stride, uint32_t* guard) {
+    const uint32_t o0 = off[a], o1 = off[a + 1];
+    if (o1 < o0 || o1 - o0 > bits_stride * 8u) {
+        if (threadIdx.x == 0 && guard) atomicOr(guard, (uint32_t)GUARD_BAD_ROW);
+        return 0xffffffffu;
+    }
+    return o1 - o0;
+}
+
 // ------------------------------------------------------------------------------------------ K2: G1 gather + aggregate
 // one block per aggregate; thread t takes members t, t+B, ...: bit test, index load, 96-byte record
 // gather (six 128-bit loads), mixed addition; then the block-level tree.
 __global__ void __launch_bounds__(128) k_g1_aggregate(const uint32_t* __restrict__ records, const uint8_t* __restrict__ valid,
                                                        const uint32_t* __restrict__ members, const uint32_t* __restrict__ off,
                                                        const uint8_t* __restrict__ bits, uint32_t bits_stride, uint32_t n_agg,
-                                                       uint32_t* out_jac, uint8_t* out_status) {
+                                                       uint32_t* out_jac, uint8_t* out_status, uint64_t n_val, uint32_t* guard) {
     __shared__ g1_jac red[4];
     const uint32_t a = blockIdx.x;
     if (a >= n_agg) return;
-    const uint32_t size = off[a + 1] - off[a];
+    uint32_t size = guarded_row_size(off, a, bits_stride, guard);
     g1_jac acc = pt_inf<fp>();
     uint32_t status = 0, cnt = 0;
+    const bool row_bad = size == 0xffffffffu;
+    if (row_bad) {
+        size = 0;
+        status = PK_BAD_INDEX;
+    }
 #pragma unroll 1
     for (uint32_t j = threadIdx.x; j < size; j += blockDim.x)
-        core_g1_accumulate(records, valid, members, off, bits, bits_stride, a, j, acc, status, cnt);
+        core_g1_accumulate(records, valid, members, off, bits, bits_stride, a, j, acc, status, cnt, n_val);
     acc = block_sum_points(acc, red);
     status = __syncthreads_or((int)status);
     cnt = __syncthreads_count(cnt != 0);
-    if (threadIdx.x == 0) core_g1_finish(acc, status, cnt, a, out_jac, out_status);
+    if (threadIdx.x == 0) {
+        if ((status & PK_BAD_INDEX) && !row_bad && guard) atomicOr(guard, (uint32_t)GUARD_BAD_INDEX);
+        core_g1_finish(acc, status, cnt, a, out_jac, out_status);
+    }
 }
 
 // Jacobian aggregated pubkeys -> compressed 48 bytes (only for the b2_g1_aggregate entry point)
@@ -166,13 +189,18 @@ __global__ void k_probe_smid(unsigned int* seen) {
 // the compressed encoding is NOT done here (127 threads would idle behind it): stage 3 does it with a thread per segment.
 __global__ void __launch_bounds__(32) k_g2_segment_sum(const uint32_t* __restrict__ aff, const uint8_t* __restrict__ st,
                                                             const uint32_t* __restrict__ seg_off, uint32_t n_seg, uint32_t* sum_jac,
-                                                            int32_t* seg_status) {
+                                                            int32_t* seg_status, uint64_t n_sig, uint32_t* guard) {
     __shared__ g2_jac red[4];
     const uint32_t s = blockIdx.x;
     if (s >= n_seg) return;
-    const uint32_t begin = seg_off[s], end = seg_off[s + 1];
+    uint32_t begin = seg_off[s], end = seg_off[s + 1];
     g2_jac acc = pt_inf<fp2>();
     uint32_t bad = 0;
+    if (end < begin || end > n_sig) {           // malformed offsets (device-pointer entry points): the segment is undecodable, nothing is read
+        if (threadIdx.x == 0 && guard) atomicOr(guard, (uint32_t)GUARD_BAD_ROW);
+        begin = end = 0;
+        bad = 1;
+    }
 #pragma unroll 1
     for (uint32_t j = begin + threadIdx.x; j < end; j += blockDim.x) {
         uint8_t f = st[j];
@@ -273,7 +301,7 @@ __device__ __forceinline__ g2_aff load_g2_aff(const uint32_t* p) {
 __global__ void __launch_bounds__(128, B2_TAIL_MIN_BLOCKS) k_miller(const uint32_t* __restrict__ pk_jac, const uint8_t* __restrict__ pk_status,
                                                 const uint32_t* __restrict__ h_aff, const uint8_t* __restrict__ hflag,
                                                 const uint32_t* __restrict__ s_aff, const uint8_t* __restrict__ sflag, uint32_t n_agg,
-                                                uint32_t* f_out, int mode) {
+                                                uint32_t* f_out, int mode, const uint8_t* __restrict__ gpass = nullptr, uint32_t group = 1) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (mode == 0) {
         if (t >= 2 * n_agg) return;
@@ -282,6 +310,7 @@ __global__ void __launch_bounds__(128, B2_TAIL_MIN_BLOCKS) k_miller(const uint32
         t = 2 * t + (uint32_t)(mode - 1);
     }
     uint32_t a = t >> 1;
+    if (gpass && gpass[a / group]) return;      // RLC fallback pass: only the members of a group whose batch equation failed
     fp12 f;
     if (t & 1) {
         f = core_miller_sig(load_g2_aff(s_aff + 48 * (uint64_t)a), sflag[a]);
@@ -294,9 +323,11 @@ __global__ void __launch_bounds__(128, B2_TAIL_MIN_BLOCKS) k_miller(const uint32
     for (int k = 0; k < 144; k++) o[k] = w[k];
 }
 __global__ void __launch_bounds__(128, B2_TAIL_MIN_BLOCKS) k_final_verdict(const uint32_t* __restrict__ f_in, const uint8_t* __restrict__ pk_status,
-                                                       const uint8_t* __restrict__ sflag, uint32_t n_agg, uint8_t* ok) {
+                                                       const uint8_t* __restrict__ sflag, uint32_t n_agg, uint8_t* ok,
+                                                       const uint8_t* __restrict__ gpass = nullptr, uint32_t group = 1) {
     uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n_agg) return;
+    if (gpass && gpass[a / group]) return;      // RLC fallback pass (see k_miller)
     fp12 f0, f1;
     uint32_t* w0 = reinterpret_cast<uint32_t*>(&f0);
     uint32_t* w1 = reinterpret_cast<uint32_t*>(&f1);
@@ -397,33 +428,49 @@ __global__ void __launch_bounds__(256) k_shuffle_apply(uint32_t n, uint32_t roun
 // order a+1, so atomicMax picks "highest epoch, earliest in list, stored wins ties" -- exactly the
 // sequential rule `i not in latest_messages or target.epoch > latest_messages[i].epoch`.
 __device__ __forceinline__ bool lmd_member(const uint32_t* members, const uint32_t* off, const uint8_t* bits, uint32_t stride, uint32_t a,
-                                           uint32_t j, uint32_t& v) {
+                                           uint32_t j, uint32_t& v, uint64_t n_val, uint32_t* guard) {
     if (!((bits[(uint64_t)a * stride + (j >> 3)] >> (j & 7)) & 1)) return false;
     v = members[off[a] + j];
+    if (v >= n_val) {
+        if (guard) atomicOr(guard, (uint32_t)GUARD_BAD_INDEX);
+        return false;
+    }
+    return true;
+}
+// row size and key of aggregate a for the LMD kernels; false: skip the aggregate (not accepted, malformed row, epoch >= 2^32 - 1)
+__device__ __forceinline__ bool lmd_row(const uint32_t* off, uint32_t stride, const uint64_t* target_epoch, const uint8_t* accept, uint32_t a,
+                                        uint32_t& size, unsigned long long& key, uint32_t* guard) {
+    if (accept && !accept[a]) return false;
+    size = guarded_row_size(off, a, stride, guard);
+    if (size == 0xffffffffu) return false;
+    const unsigned long long e = target_epoch[a];
+    if (e >= 0xffffffffull) {                   // would overflow the (epoch << 32 | order) key and break the order-exact election
+        if (threadIdx.x == 0 && guard) atomicOr(guard, (uint32_t)GUARD_BAD_EPOCH);
+        return false;
+    }
+    key = (e << 32) | (0xffffffffull - (a + 1));
     return true;
 }
 __global__ void __launch_bounds__(128) k_lmd_phase1(const uint32_t* __restrict__ members, const uint32_t* __restrict__ off,
                                                      const uint8_t* __restrict__ bits, uint32_t stride, const uint64_t* __restrict__ target_epoch,
                                                      const uint8_t* __restrict__ accept, const uint8_t* __restrict__ equiv, uint32_t n_agg,
-                                                     unsigned long long* lmd_key) {
-    uint32_t a = blockIdx.x;
-    if (a >= n_agg || (accept && !accept[a])) return;
-    unsigned long long key = ((unsigned long long)target_epoch[a] << 32) | (0xffffffffull - (a + 1));
-    uint32_t size = off[a + 1] - off[a], v;
+                                                     unsigned long long* lmd_key, uint64_t n_val, uint32_t* guard) {
+    uint32_t a = blockIdx.x, size, v;
+    unsigned long long key;
+    if (a >= n_agg || !lmd_row(off, stride, target_epoch, accept, a, size, key, guard)) return;
     for (uint32_t j = threadIdx.x; j < size; j += blockDim.x)
-        if (lmd_member(members, off, bits, stride, a, j, v) && !equiv[v]) atomicMax(&lmd_key[v], key);
+        if (lmd_member(members, off, bits, stride, a, j, v, n_val, guard) && !equiv[v]) atomicMax(&lmd_key[v], key);
 }
 __global__ void __launch_bounds__(128) k_lmd_phase2(const uint32_t* __restrict__ members, const uint32_t* __restrict__ off,
                                                      const uint8_t* __restrict__ bits, uint32_t stride, const uint64_t* __restrict__ target_epoch,
                                                      const uint32_t* __restrict__ block_idx, const uint8_t* __restrict__ accept,
                                                      const uint8_t* __restrict__ equiv, uint32_t n_agg, unsigned long long* lmd_key,
-                                                     uint32_t* lmd_block) {
-    uint32_t a = blockIdx.x;
-    if (a >= n_agg || (accept && !accept[a])) return;
-    unsigned long long key = ((unsigned long long)target_epoch[a] << 32) | (0xffffffffull - (a + 1));
-    uint32_t size = off[a + 1] - off[a], v;
+                                                     uint32_t* lmd_block, uint64_t n_val) {
+    uint32_t a = blockIdx.x, size, v;
+    unsigned long long key;
+    if (a >= n_agg || !lmd_row(off, stride, target_epoch, accept, a, size, key, nullptr)) return;
     for (uint32_t j = threadIdx.x; j < size; j += blockDim.x)
-        if (lmd_member(members, off, bits, stride, a, j, v) && !equiv[v] && lmd_key[v] == key) {
+        if (lmd_member(members, off, bits, stride, a, j, v, n_val, nullptr) && !equiv[v] && lmd_key[v] == key) {
             lmd_block[v] = block_idx[a];
             lmd_key[v] = key | 0xffffffffull;
         }

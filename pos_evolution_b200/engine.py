@@ -241,6 +241,14 @@ class Engine:
     def set_fork_choice_params(self, min_vote_epoch: int = 0, exclude_slashed: bool = False):
         self._ck(self.lib.b2_set_fork_choice_params(self.h, int(min_vote_epoch), 1 if exclude_slashed else 0))
 
+    def set_verify_mode(self, rlc: bool, seed32: bytes = None):
+        """FastAggregateVerify per aggregate (default) or in random-linear-combination batches of 32 with per-aggregate fallback
+        (same verdict vector, about half the pairing work).  seed32: the verifier's secret randomness (os.urandom when None)."""
+        import os
+        seed = np.frombuffer(bytes(seed32) if seed32 is not None else os.urandom(32), dtype=np.uint8)
+        assert seed.shape == (32,)
+        self._ck(self.lib.b2_set_verify_mode(self.h, 1 if rlc else 0, _p(seed) if rlc else None))
+
     def on_attester_slashing(self, indices_1, indices_2):
         """Store.equivocating_indices |= set(indices_1) & set(indices_2)   (pos-evolution.md:1459-1461); both lists sorted."""
         a, b = _c(indices_1, np.uint32), _c(indices_2, np.uint32)
@@ -292,7 +300,8 @@ class Engine:
     def epoch_dev(self, d_sigs, d_members, d_off, d_bits, d_msgs, d_target_epoch, d_block_idx, d_agg_sig, d_agg_status, d_ok):
         n_agg = d_off.numel() - 1
         self._ck(self.lib.b2_epoch_dev(self.h, d_sigs.data_ptr(), d_members.data_ptr(), d_off.data_ptr(), d_bits.data_ptr(), d_bits.shape[1],
-                                       d_msgs.data_ptr(), d_target_epoch.data_ptr(), d_block_idx.data_ptr(), n_agg, d_sigs.numel() // 96,
+                                       d_msgs.data_ptr(), d_target_epoch.data_ptr() if d_target_epoch is not None else None,
+                                       d_block_idx.data_ptr() if d_block_idx is not None else None, n_agg, d_sigs.numel() // 96,
                                        d_agg_sig.data_ptr(), d_agg_status.data_ptr(), d_ok.data_ptr(), self._stream()))
 
     def epoch_start_dev(self, slot, d_sigs, d_members, d_off, d_bits, d_msgs, d_agg_status):
@@ -302,9 +311,11 @@ class Engine:
 
     def epoch_tail_dev(self, slot, d_members, d_off, d_bits, d_target_epoch, d_block_idx, d_agg_sig, d_agg_status, d_ok):
         n_agg = d_off.numel() - 1
+        """d_target_epoch / d_block_idx None: no LMD update in the tail (sharded epoch: the caller applies it after the verdict exchange)."""
         self._ck(self.lib.b2_epoch_tail_dev(self.h, int(slot), d_members.data_ptr(), d_off.data_ptr(), d_bits.data_ptr(), d_bits.shape[1],
-                                            d_target_epoch.data_ptr(), d_block_idx.data_ptr(), n_agg, d_agg_sig.data_ptr(), d_agg_status.data_ptr(),
-                                            d_ok.data_ptr()))
+                                            d_target_epoch.data_ptr() if d_target_epoch is not None else None,
+                                            d_block_idx.data_ptr() if d_block_idx is not None else None, n_agg, d_agg_sig.data_ptr(),
+                                            d_agg_status.data_ptr(), d_ok.data_ptr()))
 
     def epoch_set_pairing_form(self, team: bool):
         self._ck(self.lib.b2_epoch_set_pairing_form(self.h, 1 if team else 0))
@@ -314,6 +325,22 @@ class Engine:
 
     def vote_weights_dev(self, d_votes):
         self._ck(self.lib.b2_vote_weights_dev(self.h, d_votes.data_ptr(), self._stream()))
+
+    def vote_weights_range_dev(self, v_begin, v_end, d_votes):
+        """direct votes of the validators [v_begin, v_end) only (this rank's shard of one validator set)"""
+        self._ck(self.lib.b2_vote_weights_range_dev(self.h, int(v_begin), int(v_end), d_votes.data_ptr(), self._stream()))
+
+    def gather_probe_dev(self, d_members, d_off, d_bits, d_checksum, tma: bool = True):
+        """gather stage of K2 alone: d_checksum[a] = XOR of the pubkey-record words aggregate a selects (TMA-staged or plain-load form)"""
+        n_agg = d_off.numel() - 1
+        self._ck(self.lib.b2_gather_probe_dev(self.h, d_members.data_ptr(), d_off.data_ptr(), d_bits.data_ptr(), d_bits.shape[1], n_agg,
+                                              1 if tma else 0, d_checksum.data_ptr(), self._stream()))
+
+    def guard_flags(self) -> int:
+        """synchronise; return and clear the device-side input guard word (B2_GUARD_* bits) of the *_dev entry points"""
+        out = ctypes.c_uint32(0)
+        self._ck(self.lib.b2_guard_flags(self.h, ctypes.byref(out)))
+        return int(out.value)
 
     def head_from_votes_dev(self, d_votes, d_head, justified_idx=0, boost_idx=-1, boost_score=0, d_weight=None):
         self._ck(self.lib.b2_head_from_votes_dev(self.h, d_votes.data_ptr(), int(justified_idx), int(boost_idx), int(boost_score),

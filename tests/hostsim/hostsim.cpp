@@ -237,3 +237,36 @@ extern "C" void hs_team_final_exp(const uint32_t* in, uint32_t* out) {
 }
 
 extern "C" void hs_signing_root(const uint8_t* data128, const uint8_t* domain32, uint8_t* out32) { attestation_signing_root(data128, domain32, out32); }
+
+// ---- random-linear-combination batch verification: one group, the same per-thread bodies the kernels of csrc/rlc.cuh run
+extern "C" int hs_rlc_group(const uint8_t* seed32, const uint8_t* pk48, const uint8_t* msg32, const uint8_t* sig96, uint32_t n, uint64_t* r_out,
+                            uint8_t* in_batch_out, uint8_t* gpass) {
+    if (n == 0 || n > 32) return 1;
+    fp12* f_pk = new fp12[n];
+    g2_jac ssum = pt_inf<fp2>();
+    for (uint32_t i = 0; i < n; i++) {
+        g1_aff pa;
+        pa.x = fp_zero();
+        pa.y = fp_zero();
+        int sp = g1_decompress(pk48 + 48 * i, pa);
+        uint8_t pk_status = (sp == DEC_OK && pt_in_subgroup_exact(pt_from_affine(pa))) ? PK_OK : PK_INVALID_KEY;
+        g2_aff h, s;
+        uint8_t hflag, sflag;
+        core_hash_msg(msg32, i, h, hflag);
+        core_sig_prepare(sig96, i, s, sflag);
+        const uint64_t r = core_rlc_scalar(seed32, i, msg32 + 32 * i);
+        r_out[i] = r;
+        in_batch_out[i] = rlc_in_batch(pk_status, sflag) ? 1 : 0;
+        f_pk[i] = fp12_one();
+        if (pk_status == PK_OK) f_pk[i] = miller_loop(pt_mul_var64(pt_from_affine(pa), r), h, hflag != 0);
+        if (pk_status == PK_OK && sflag == SIG_OK) ssum = pt_add(ssum, pt_mul_var64_aff(s, r));
+    }
+    g2_aff sa;
+    sa.x = fp2_zero();
+    sa.y = fp2_zero();
+    const bool finite = pt_to_affine(ssum, sa);
+    fp12 f_sig = core_miller_sig(sa, finite ? SIG_OK : SIG_INFINITY);
+    *gpass = core_rlc_group_verdict(f_sig, f_pk, in_batch_out, n);
+    delete[] f_pk;
+    return 0;
+}

@@ -189,6 +189,42 @@ def test_fast_aggregate_verify_vs_oracle(eng, world):
     ok2 = eng.fast_aggregate_verify_pks(np.frombuffer(b"".join(flat), dtype=np.uint8), poff,
                                         np.frombuffer(b"".join(msgs), dtype=np.uint8), np.frombuffer(b"".join(sigs), dtype=np.uint8))
     assert ok2.tolist() == [int(e) for e in expect]
+    # random-linear-combination batch mode: the same verdict vector (this batch is ONE group with rejected members: its equation
+    # fails and every member is decided by the per-aggregate fallback), for both entry points, for two different seeds
+    for seed in (b"seed-1", b"seed-2"):
+        eng.set_verify_mode(True, hashlib.sha256(seed).digest())
+        try:
+            ok3 = eng.fast_aggregate_verify(members, off, _bits(rows), np.frombuffer(b"".join(msgs), dtype=np.uint8),
+                                            np.frombuffer(b"".join(sigs), dtype=np.uint8))
+            ok4 = eng.fast_aggregate_verify_pks(np.frombuffer(b"".join(flat), dtype=np.uint8), poff,
+                                                np.frombuffer(b"".join(msgs), dtype=np.uint8), np.frombuffer(b"".join(sigs), dtype=np.uint8))
+        finally:
+            eng.set_verify_mode(False)
+        assert ok3.tolist() == [int(e) for e in expect] and ok4.tolist() == [int(e) for e in expect]
+    # groups that pass as a whole: the three honest aggregates repeated 24 times = 72 aggregates = 3 groups (32 + 32 + 8), no
+    # fallback; then one corrupted signature in the middle group: exactly that aggregate flips
+    hm, ho, hr, hmsg, hsig = [], [0], [], [], []
+    for rep in range(24):
+        for a in range(3):
+            hm += members[off[a]:off[a + 1]]
+            ho.append(len(hm))
+            hr.append(rows[a])
+            hmsg.append(msgs[a])
+            hsig.append(sigs[a])
+    eng.set_verify_mode(True, hashlib.sha256(b"seed-3").digest())
+    try:
+        okh = eng.fast_aggregate_verify(hm, ho, _bits(hr), np.frombuffer(b"".join(hmsg), dtype=np.uint8), np.frombuffer(b"".join(hsig), dtype=np.uint8))
+        assert okh.tolist() == [1] * 72
+        hsig[40] = hsig[41]                              # a valid signature, of another message / committee
+        okh = eng.fast_aggregate_verify(hm, ho, _bits(hr), np.frombuffer(b"".join(hmsg), dtype=np.uint8), np.frombuffer(b"".join(hsig), dtype=np.uint8))
+        assert okh.tolist() == [1] * 40 + [0] + [1] * 31
+        # swapping two signatures inside a group keeps sum S_i: only the random scalars catch it
+        hsig[40] = hsig[37]
+        hsig[3], hsig[4] = hsig[4], hsig[3]
+        okh = eng.fast_aggregate_verify(hm, ho, _bits(hr), np.frombuffer(b"".join(hmsg), dtype=np.uint8), np.frombuffer(b"".join(hsig), dtype=np.uint8))
+        assert okh.tolist() == [1] * 3 + [0, 0] + [1] * 67
+    finally:
+        eng.set_verify_mode(False)
 
 
 def test_aggregate_then_verify_linearity_512(eng):

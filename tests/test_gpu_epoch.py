@@ -72,9 +72,19 @@ def _expected(pks, members, off, msgs, bits, sigs):
     return aggs, oks
 
 
-@pytest.mark.parametrize("mode,depth", [("sync", 3), ("pipelined", 2), ("pipelined", 3), ("pipelined", 4), ("pipelined_host", 3), ("pipelined_host", 2),
-                                        ("sync_host", 3)])
+@pytest.mark.parametrize("mode,depth", [("sync", 3), ("pipelined", 2), ("pipelined", 3), ("pipelined", 4), ("pipelined", 8), ("pipelined_host", 3),
+                                        ("pipelined_host", 2), ("sync_host", 3), ("pipelined_team", 6), ("sync_rlc", 3), ("pipelined_rlc", 3),
+                                        ("pipelined_host_rlc", 4)])
 def test_epoch_pipeline_matches_oracle(mode, depth):
+    """*_rlc: the same epochs with FastAggregateVerify in random-linear-combination batches (b2_set_verify_mode): the three rejected
+    aggregates sit in the only group, so its equation fails and every member is decided by the per-aggregate fallback;
+    pipelined_team: the always-team tail a sharded rank uses."""
+    rlc = mode.endswith("_rlc")
+    if rlc:
+        mode = mode[:-4]
+    tail_form = "team" if mode == "pipelined_team" else "thread"
+    if mode == "pipelined_team":
+        mode = "pipelined"
     from pos_evolution_b200.engine import Engine
     from pos_evolution_b200.epoch import EpochProcessor
     pks, members, off, tree, eff = _world()
@@ -84,7 +94,9 @@ def test_epoch_pipeline_matches_oracle(mode, depth):
     eng.tree_load(parent, slot, roots, leaf_viable)
     eng.latest_messages_reset()
     dev = torch.device("cuda", 0)
-    ep = EpochProcessor(eng, N_AGG, N_AGG * CSIZE, 1, N_BLK, device=dev, depth=depth)
+    if rlc:
+        eng.set_verify_mode(True, hashlib.sha256(b"test-seed").digest())
+    ep = EpochProcessor(eng, N_AGG, N_AGG * CSIZE, 1, N_BLK, device=dev, depth=depth, tail_form=tail_form)
     ep.set_committees(members, off)
     rng = np.random.default_rng(3)
 

@@ -109,3 +109,75 @@ def test_full_epoch_properties(full):
     assert int(tickets[-1][0].sum().item()) == N_AGG
     e, b, h = eng.latest_messages_read()
     assert np.array_equal(h, has_msg) and np.array_equal(e[h == 1], m_epoch[h == 1]) and np.array_equal(b[h == 1], msg_block[h == 1])
+
+
+# ------------------------------------------------------------------------------------------ bytes, not only properties
+# The keys of the synthetic world are an arithmetic progression sk_i = sk0 + i*delta, so for any set S of
+# validators the oracle knows the aggregate pubkey SkToPk(sum sk_i) and the aggregate signature Sign(sum sk_i, m) without
+# adding 512 points in pure Python.  These tests compare the BYTES the GPU produces at full size with those oracle values.
+def test_aggregate_signature_bytes_vs_oracle_linearity(full):
+    """bls.Aggregate at full size: 64 of the 2 048 committee aggregates (every 32nd), byte for byte against the oracle."""
+    eng, W, bench = full
+    from oracle import bls_sig as B
+    agg, st = eng.aggregate(W["sigs"], W["off"])
+    assert not st.any()
+    for a in range(0, bench.N_AGG, 32):
+        want = B.Sign(bench.committee_secret_sum(W, a), bytes(W["msgs"][a]))
+        assert bytes(agg[a]) == want, a
+
+
+def test_config2_bls_aggregate_32768_signatures(full):
+    """BASELINE.json config 2: 32 768 signatures -> 64 segments of 512; all 64 outputs == oracle.Sign(sum sk, m_c)."""
+    eng, W, bench = full
+    from oracle import bls_sig as B
+    n2 = 64 * bench.COMMITTEE_SIZE
+    agg, st = eng.aggregate(W["sigs"][:n2], W["off"][:65])
+    assert not st.any()
+    for a in range(64):
+        assert bytes(agg[a]) == B.Sign(bench.committee_secret_sum(W, a), bytes(W["msgs"][a])), a
+    # ragged segmentation of the same signatures: 3 uneven segments + an empty one (status 2), checksum of checksums
+    seg = np.array([0, 1, 700, 700, n2], dtype=np.uint32)
+    agg_r, st_r = eng.aggregate(W["sigs"][:n2], seg)
+    assert st_r.tolist() == [0, 0, 2, 0]
+    tot, st_t = eng.aggregate(agg_r[[0, 1, 3]], np.array([0, 3], dtype=np.uint32))
+    tot2, st_t2 = eng.aggregate(agg, np.array([0, 64], dtype=np.uint32))
+    assert int(st_t[0]) == 0 and int(st_t2[0]) == 0 and bytes(tot[0]) == bytes(tot2[0])
+
+
+@pytest.mark.parametrize("frac,seed", [(0.99, 1), (0.5, 2)])
+def test_k2_partial_participation_bytes_vs_oracle(full, frac, seed):
+    """K2 (b2_g1_aggregate, the TMA-staged gather) on 512-member committees at 99 % / 50 % random participation: the compressed
+    aggregate pubkey of 48 committees == oracle.SkToPk(sum of the selected secret keys)."""
+    eng, W, bench = full
+    from oracle import bls_sig as B
+    rng = np.random.default_rng(seed)
+    sel = rng.random((bench.N_AGG, bench.COMMITTEE_SIZE)) < frac
+    sel[:, 0] = True
+    bits = np.packbits(sel, axis=1, bitorder="little")
+    out, status = eng.g1_aggregate(W["members"], W["off"], bits)
+    assert not status.any()
+    for a in list(range(0, bench.N_AGG, 64)) + [1, 2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 2047]:
+        assert bytes(out[a]) == B.SkToPk(bench.committee_secret_sum(W, a, bits[a])), a
+
+
+@pytest.mark.parametrize("name,frac,seed", [("100pct", 1.0, 0), ("99pct", 0.99, 1), ("50pct", 0.5, 2)])
+def test_config3_participation_and_corruption(full, name, frac, seed):
+    """BASELINE.json config 3: 2 048 x 512 FastAggregateVerify at 100 / 99 / 50 % participation with 1 % of the
+    aggregates corrupted: exactly the corrupted ones are rejected; the aggregate signatures of the selected subsets (made by
+    the GPU's bls.Aggregate) equal the oracle's Sign(sum of selected sk, m) on a sample."""
+    eng, W, bench = full
+    from oracle import bls_sig as B
+    bits, agg, expect = bench.participation_case(eng, W, np, frac, seed)
+    ok = eng.fast_aggregate_verify(W["members"], W["off"], bits, W["msgs"], agg)
+    assert np.array_equal(ok, expect)
+    assert int((expect == 0).sum()) == 20
+    # the same batch through the random-linear-combination mode: every corrupted aggregate is still individually identified
+    eng.set_verify_mode(True, bytes(range(32)))
+    try:
+        ok_rlc = eng.fast_aggregate_verify(W["members"], W["off"], bits, W["msgs"], agg)
+    finally:
+        eng.set_verify_mode(False)
+    assert np.array_equal(ok_rlc, expect)
+    good = [a for a in range(0, bench.N_AGG, 256) if expect[a]]
+    for a in good:
+        assert bytes(agg[a]) == B.Sign(bench.committee_secret_sum(W, a, bits[a]), bytes(W["msgs"][a])), a

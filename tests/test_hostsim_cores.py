@@ -97,3 +97,40 @@ def test_signing_root_core_matches_oracle():
         out = ctypes.create_string_buffer(32)
         lib.hs_signing_root(hs.buf(ser), hs.buf(dom), out)
         assert out.raw == OS.Spec.compute_signing_root(d, dom)
+
+
+def test_rlc_group_equation_on_the_host():
+    """The random-linear-combination batch equation (csrc/cores.cuh, kernels in csrc/rlc.cuh) with the device code compiled for the
+    host: scalars == SHA-256(seed || LE32(i) || msg)[0:8] | 1; a group of honest (pk, msg, sig) triples passes; replacing one
+    signature by a valid signature of another message, or one key by another valid key, fails the group; an undecodable
+    signature is rejected outright (not part of the equation) and the rest still passes."""
+    import ctypes
+    import hashlib
+    from oracle import bls_sig as B
+    lib = hs.load()
+    seed = hashlib.sha256(b"rlc-seed").digest()
+    n = 3
+    sks = [scenarios.secret_key(i) for i in range(n)]
+    msgs = [hashlib.sha256(bytes([i])).digest() for i in range(n)]
+    pks = [B.SkToPk(k) for k in sks]
+    sigs = [B.Sign(k, m) for k, m in zip(sks, msgs)]
+
+    def run(pks_, sigs_):
+        r = (ctypes.c_uint64 * n)()
+        inb = (ctypes.c_uint8 * n)()
+        gp = ctypes.c_uint8(9)
+        rc = lib.hs_rlc_group(hs.buf(seed), hs.buf(b"".join(pks_)), hs.buf(b"".join(msgs)), hs.buf(b"".join(sigs_)), n, r, inb, ctypes.byref(gp))
+        assert rc == 0
+        return list(r), list(inb), int(gp.value)
+
+    r, inb, gp = run(pks, sigs)
+    for i in range(n):
+        want = int.from_bytes(hashlib.sha256(seed + i.to_bytes(4, "little") + msgs[i]).digest()[:8], "little") | 1
+        assert r[i] == want
+    assert inb == [1, 1, 1] and gp == 1
+    assert run(pks, [sigs[0], B.Sign(sks[1], msgs[2]), sigs[2]])[2] == 0          # wrong message under one signature
+    assert run([pks[0], pks[2], pks[2]], sigs)[2] == 0                            # wrong key
+    r2, inb2, gp2 = run(pks, [sigs[0], bytes(96), sigs[2]])                       # undecodable signature: rejected outright
+    assert inb2 == [1, 0, 1] and gp2 == 1
+    # a swap of two signatures between members keeps sum S_i but not sum r_i S_i: the random scalars are what catches it
+    assert run(pks, [sigs[1], sigs[0], sigs[2]])[2] == 0
