@@ -282,6 +282,8 @@ def run_gpu(args):
     shard = (rank, world) if (strong and world > 1) else None
     depth = args.depth or ({1: 3, 2: 4, 4: 6}.get(world, 8) if strong else 3)
     eng = Engine(local)
+    if args.rlc:
+        eng.set_verify_mode(True)                      # FastAggregateVerify in random-linear-combination batches (fresh os.urandom seed)
     W = build_world(eng, rank, np, PS, shard=shard)
     ep = EpochProcessor(eng, N_AGG, N_VAL, COMMITTEE_SIZE // 8, N_BLOCKS, process_group=pg, device=dev, depth=depth, shard=shard, n_validators=N_VAL)
     ep.set_committees(W["members"], W["off"])
@@ -522,6 +524,7 @@ def run_gpu(args):
                        "validators_total": total_units, "aggregates_per_rank": ep.n_loc, "signatures_per_rank": n_loc_sig, "parallelism": par,
                        "pipeline_depth": depth, "pipelining": "software pipeline over pipeline_depth slots: epoch k+1's signature decompression overlaps the pairing tails of the epochs before it; all K results complete inside the timed region (fill and drain included)",
                        "tail_form": "team" if ep.always_team else "thread (team for the last epoch of the batch)",
+                       "verify_mode": "rlc batches of 32 with per-aggregate fallback" if args.rlc else "per aggregate",
                        "l2": "per-step working set ~0.5 GB/world (signatures 101 MB + decompressed points 201 MB) + registry 101 MB > 126 MB L2"},
             "e2e": {"value": total_units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": ep.h2d_bytes, "d2h_bytes_per_step": ep.d2h_bytes,
                     "d2h": "verdicts + head index + the 2048 aggregate signatures"},
@@ -542,7 +545,9 @@ def run_gpu(args):
                                     "l2": "flushed before every launch (512 MB memset): the 100.7 MB registry would otherwise stay in the 126 MB L2",
                                     "ms": g_tma_cold, "ms_best": g_tma_cold_min, "frac_best": gbps(g_tma_cold_min) / peak,
                                     "l2_warm": {"ms": g_tma_warm, "achieved": gbps(g_tma_warm), "frac": gbps(g_tma_warm) / peak},
-                                    "plain_ldg_form": {"ms": g_ldg_cold, "ms_best": g_ldg_cold_min, "achieved": gbps(g_ldg_cold), "frac": gbps(g_ldg_cold) / peak},
+                                    "plain_ldg_form": {"kernel": "k_g1_gather_ldg_probe: block per aggregate, six lanes per 96-B record (LDG.E.128), all loads of a thread in flight -- the fastest of the six forms of tools/gather_bench.cu (profiles/r2_gather_microbench.jsonl)",
+                                                       "ms": g_ldg_cold, "ms_best": g_ldg_cold_min, "achieved": gbps(g_ldg_cold), "frac": gbps(g_ldg_cold) / peak, "frac_best": gbps(g_ldg_cold_min) / peak},
+                                    "what_binds": "random 96-byte reads: HBM moves two 64-byte bursts (128 B) per record, i.e. 1.33x the algorithmic bytes, at random-access row-buffer efficiency; with the additions K2 is bound by the integer multiply pipe (34 MAC/B), not by this stage",
                                     "checksums_equal": True}},
             "setup_s": W["setup_s"],
         }
@@ -586,6 +591,7 @@ def main():
     ap.add_argument("--depth", type=int, default=0, help="epochs in flight in the software pipeline (2..8); 0 = 3 on one GPU, 4/6/8 on 2/4/8 GPUs of a sharded epoch")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = ONE 2^20-validator epoch sharded by slot over the ranks (north_star configs 4/5); weak = an own epoch per rank")
+    ap.add_argument("--rlc", action="store_true", help="FastAggregateVerify in random-linear-combination batches (b2_set_verify_mode 1)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the per-config numbers of BASELINE.json configs 2 and 3")
     ap.add_argument("--probe-overlap", action="store_true",
                     help="also time bls.Aggregate and FastAggregateVerify running concurrently on two streams (diagnostic)")

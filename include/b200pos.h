@@ -53,6 +53,9 @@ uint64_t b2_launch_count(b2_ctx* ctx);
  * (is_active_validator), bit1 = slashed.  pk_valid_out (may be NULL): 1 = KeyValidate passed. */
 int b2_registry_load(b2_ctx* ctx, const uint8_t* pk48, const uint64_t* effective_balance, const uint8_t* flags,
                      uint64_t n_validators, uint8_t* pk_valid_out);
+/* bls.KeyValidate (decodable, not infinity, in the r-torsion; eth2spec.utils.bls, used by process_deposit upstream) for n explicit
+ * pubkeys; leaves the registry alone. */
+int b2_key_validate(b2_ctx* ctx, const uint8_t* pk48, uint64_t n, uint8_t* valid_out);
 /* refresh balances / flags only (process_effective_balance_updates, pos-evolution.md:122-133, changes them per epoch) */
 int b2_registry_update_balances(b2_ctx* ctx, const uint64_t* effective_balance, const uint8_t* flags, uint64_t n_validators);
 
@@ -215,7 +218,7 @@ int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members,
 int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                        uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, void* stream);
 int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
-                      const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
+                      const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, int32_t* d_agg_status,
                       uint8_t* d_ok_out);
 int b2_epoch_wait_dev(b2_ctx* ctx, int slot, void* stream);
 /* Which form of the pairing kernels (K5/K6) b2_epoch_start_dev / b2_epoch_tail_dev enqueue from now on: 0 = thread per aggregate
@@ -234,6 +237,8 @@ int b2_vote_weights_range_dev(b2_ctx* ctx, uint64_t v_begin, uint64_t v_end, uin
 int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
                            uint64_t* d_weight_out /* may be NULL */, uint32_t* d_head_idx_out, void* stream);
 uint32_t b2_tree_size(b2_ctx* ctx);
+/* profiling aid: SM-clock stamps of the phases of the context's last get_head (vote scatter of CTA 0, tree phases); u64[32] */
+int b2_debug_head_clocks(b2_ctx* ctx, uint64_t* out32);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,8 @@ import os
 from ctypes import POINTER, c_char_p, c_int, c_int32, c_uint8, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200pos.so")
+# B2_LIB: load another build of the SAME library (tools/sanitize.sh: the ASan/UBSan-instrumented host side); not a fallback
+LIB_PATH = os.environ.get("B2_LIB") or os.path.join(HERE, "libb200pos.so")
 
 B2_OK, B2_EINVAL, B2_ECUDA, B2_ENODEVICE, B2_ENOMEM = 0, -1, -2, -3, -4
 _ERRNAMES = {B2_EINVAL: "B2_EINVAL", B2_ECUDA: "B2_ECUDA", B2_ENODEVICE: "B2_ENODEVICE", B2_ENOMEM: "B2_ENOMEM"}
@@ -29,6 +30,7 @@ SIGNATURES = {
     "b2_sync": (c_int, [c_void_p]),
     "b2_launch_count": (c_uint64, [c_void_p]),
     "b2_registry_load": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
+    "b2_key_validate": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
     "b2_registry_update_balances": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64]),
     "b2_g1_aggregate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_void_p, c_void_p]),
     "b2_aggregate": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]),
@@ -71,6 +73,7 @@ SIGNATURES = {
     "b2_gather_probe_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_int, c_void_p, c_void_p]),
     "b2_head_from_votes_dev": (c_int, [c_void_p, c_void_p, c_uint32, c_int32, c_uint64, c_void_p, c_void_p, c_void_p]),
     "b2_tree_size": (c_uint32, [c_void_p]),
+    "b2_debug_head_clocks": (c_int, [c_void_p, c_void_p]),
 }
 
 

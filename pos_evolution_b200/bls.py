@@ -75,15 +75,12 @@ def Verify(PK: bytes, message: bytes, signature: bytes) -> bool:
 
 
 def KeyValidate(pubkey: bytes) -> bool:
-    """decodable, not infinity, in G1 -- answered by the registry loader's validity byte."""
+    """decodable, not infinity, in G1 (b2_key_validate: the registry loader's kernel on a scratch buffer; the shared engine's
+    registry is left alone)."""
     pk = bytes(pubkey)
     if len(pk) != 48:
         return False
-    e = Engine(engine().device)            # scratch context: must not clobber the shared engine's registry
-    try:
-        return bool(e.registry_load(np.frombuffer(pk, dtype=np.uint8), np.zeros(1, dtype=np.uint64))[0])
-    finally:
-        e.close()
+    return bool(engine().key_validate(np.frombuffer(pk, dtype=np.uint8))[0])
 
 
 def Aggregate(signatures: Sequence[bytes]) -> bytes:

@@ -30,5 +30,21 @@ def build(force=False, verbose=False):
     return OUT
 
 
+ASAN_OUT = os.path.join(HERE, "libb200pos_asan.so")
+
+
+def build_asan():
+    """The same library with the HOST side (argument checks, marshaling, std::vector staging of the C ABI) instrumented by
+    AddressSanitizer + UBSan; device code unchanged.  Test tooling (tools/sanitize.sh loads it through B2_LIB), never the product."""
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC",
+           "-Xcompiler", "-fsanitize=address", "-Xcompiler", "-fsanitize=undefined", "-Xcompiler", "-fno-omit-frame-pointer", "-Xcompiler", "-g",
+           "-o", ASAN_OUT, SRC, "-ldl", "-Xlinker", "-lasan", "-Xlinker", "-lubsan"]
+    subprocess.check_call(cmd)
+    return ASAN_OUT
+
+
 if __name__ == "__main__":
-    print(build(force=True, verbose="-v" in sys.argv))
+    if "--asan" in sys.argv:
+        print(build_asan())
+    else:
+        print(build(force=True, verbose="-v" in sys.argv))

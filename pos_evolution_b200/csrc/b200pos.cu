@@ -24,6 +24,9 @@ struct dbuf {
 
 struct vslot {
     dbuf haff, hflag, pkjac, pkst, saff, sflag, f, sumjac;
+    dbuf g2aff, g2st;                                      // the slot's own decompressed signatures (pipelined epochs, B2_SEGSUM_TAIL)
+    uint64_t n_sig_tail = 0;                               // signatures of the epoch whose segment sums the tail still has to run
+    bool segsum_pending = false;
     dbuf pkjac_r, rscal, sg_aff, sg_flag, f_g, gpass;      // RLC batch mode: [r]PK, r, per-group signature sums, group Miller values / verdicts
     cudaEvent_t ev_join0 = nullptr, ev_join1 = nullptr, ev_seg = nullptr, ev_tail_done = nullptr, ev_fork = nullptr;
     cudaStream_t s_tail = nullptr;      // the slot's own tail stream: tails of consecutive epochs overlap each other
@@ -58,6 +61,13 @@ struct b2_ctx {
     unsigned k2_block = 32;    // threads per aggregate of k_g1_aggregate under the epoch pipeline (B2_K2_BLOCK: 32/64/128)
     // K2 through the TMA-staged gather kernel (gather.cuh) instead of the LDG form; B2_K2_TMA=0 selects the LDG form (A/B, profiles/)
     bool k2_tma = true;
+    // sliding-window tables of the decompression's exponentiations: B2_POW_SMEM=1 puts them in shared memory (halves the kernel's DRAM
+    // traffic, 1.40 -> 0.73 GB per launch, ncu profiles/r2_g2_decompress_raw.csv) -- but the 48 KB per block compete with the tail
+    // kernels' shared memory under the pipeline and the step is 0.6 ms SLOWER (36.11 vs 35.48 ms, profiles/r2_ab_*.json), so the
+    // default keeps them in local memory
+    bool pow_smem = false;
+    // pipelined epochs: per-segment signature sums on the slot's tail stream instead of the caller's (B2_SEGSUM_TAIL=0: round-1 form)
+    bool segsum_tail = true;
     // FastAggregateVerify mode: 0 = one pairing check per aggregate; 1 = random-linear-combination batches of B2_RLC_GROUP
     // aggregates with per-aggregate fallback (b2_set_verify_mode); d_rlc_seed = the verifier's secret 32-byte seed
     int verify_mode = 0;
@@ -71,6 +81,13 @@ struct b2_ctx {
     unsigned reserve_sms = 0;
     sm_mask reserved = {{0, 0, 0, 0}};
     unsigned long long* d_dec_counter = nullptr;      // one work counter per epoch slot
+    // one-launch get_head (k_get_head_fused): ticket counter, and the result slot in mapped pinned host memory (head, sequence)
+    bool head_fused = true;                           // B2_HEAD_FUSED=0: the two-launch + memcpy form of round 1
+    unsigned int* d_ticket = nullptr;
+    volatile uint32_t* h_head = nullptr;
+    uint32_t* d_head_host = nullptr;
+    uint32_t head_seq = 0;
+    unsigned long long* d_dbg = nullptr;              // clock64() stamps of the last get_head's phases (b2_debug_head_clocks)
     uint32_t* d_guard = nullptr;                      // device-side input guard word (kernels.cuh GuardBits), read by b2_guard_flags
     unsigned long long fc_min_key = 0;
     int fc_exclude_slashed = 0;
@@ -188,6 +205,8 @@ int b2_init(int device, b2_ctx** out) {
         if (v == 32 || v == 64 || v == 128) ctx->k2_block = v;
     }
     if (const char* e = getenv("B2_K2_TMA")) ctx->k2_tma = atoi(e) != 0;
+    if (const char* e = getenv("B2_POW_SMEM")) ctx->pow_smem = atoi(e) != 0;
+    if (const char* e = getenv("B2_SEGSUM_TAIL")) ctx->segsum_tail = atoi(e) != 0;
     if (const char* e = getenv("B2_PAIRING_FORM")) ctx->pairing_form = !strcmp(e, "team") ? 1 : (!strcmp(e, "thread") ? 2 : 0);
     if (const char* e = getenv("B2_RESERVE_SMS")) {
         unsigned v = (unsigned)atoi(e);
@@ -195,6 +214,17 @@ int b2_init(int device, b2_ctx** out) {
     }
     if (ctx->reserve_sms >= (unsigned)ctx->n_sm / 2) ctx->reserve_sms = ctx->n_sm / 9;
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_dec_counter, sizeof(unsigned long long) * B2_EPOCH_SLOTS);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_dbg, 32 * 8);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_dbg, 0, 32 * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ticket, 64);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_ticket, 0, 64);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_head, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        memset((void*)ctx->h_head, 0, 64);
+        e = cudaHostGetDevicePointer((void**)&ctx->d_head_host, (void*)ctx->h_head, 0);
+    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_get_head_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (const char* ev = getenv("B2_HEAD_FUSED")) ctx->head_fused = atoi(ev) != 0;
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_rlc_seed, 32);
     if (e == cudaSuccess) e = cudaMemset(ctx->d_rlc_seed, 0, 32);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_guard, 256);
@@ -252,7 +282,7 @@ void b2_destroy(b2_ctx* ctx) {
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < B2_EPOCH_SLOTS; i++) {
         vslot& V = ctx->slot[i];
-        dbuf* vb[] = {&V.haff, &V.hflag, &V.pkjac, &V.pkst, &V.saff, &V.sflag, &V.f, &V.sumjac, &V.pkjac_r, &V.rscal, &V.sg_aff, &V.sg_flag, &V.f_g, &V.gpass};
+        dbuf* vb[] = {&V.haff, &V.hflag, &V.pkjac, &V.pkst, &V.saff, &V.sflag, &V.f, &V.sumjac, &V.pkjac_r, &V.rscal, &V.sg_aff, &V.sg_flag, &V.f_g, &V.gpass, &V.g2aff, &V.g2st};
         for (dbuf* b : vb)
             if (b->p) cudaFree(b->p);
         cudaEvent_t evs[5] = {V.ev_join0, V.ev_join1, V.ev_seg, V.ev_tail_done, V.ev_fork};
@@ -267,6 +297,9 @@ void b2_destroy(b2_ctx* ctx) {
     if (ctx->d_dec_counter) cudaFree(ctx->d_dec_counter);
     if (ctx->d_guard) cudaFree(ctx->d_guard);
     if (ctx->d_rlc_seed) cudaFree(ctx->d_rlc_seed);
+    if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+    if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+    if (ctx->h_head) cudaFreeHost((void*)ctx->h_head);
     if (ctx->ev_votes_done) cudaEventDestroy(ctx->ev_votes_done);
     delete ctx;
 }
@@ -326,6 +359,24 @@ int b2_registry_load(b2_ctx* ctx, const uint8_t* pk48, const uint64_t* eff, cons
         ctx->d_part_first = nullptr;
     }
     ctx->n_val = n;
+    return B2_OK;
+}
+
+// bls.KeyValidate for n explicit pubkeys, without touching the registry (scratch buffers only)
+int b2_key_validate(b2_ctx* ctx, const uint8_t* pk48, uint64_t n, uint8_t* valid_out) {
+    B2_NVTX;
+    REQUIRE(ctx && pk48 && valid_out && n > 0 && n < (1ull << 32), "key_validate: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    int rc;
+    if ((rc = ensure(ctx, ctx->in_a, n * 48)) || (rc = ensure(ctx, ctx->sc_rec, n * 96 + 16)) || (rc = ensure(ctx, ctx->sc_val, n + 16))) return rc;
+    CK(cudaMemcpyAsync(ctx->in_a.p, pk48, n * 48, cudaMemcpyHostToDevice, s));
+    k_g1_decompress_validate<<<blocks_for(n, 128), 128, 0, s>>>((const uint8_t*)ctx->in_a.p, n, (uint32_t*)ctx->sc_rec.p, (uint8_t*)ctx->sc_val.p);
+    CKL(ctx);
+    std::vector<uint8_t> tmp(n);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->sc_val.p, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(valid_out, tmp.data(), n);
     return B2_OK;
 }
 
@@ -424,7 +475,7 @@ int b2_gather_probe_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* 
         k_g1_gather_tma<true><<<blocks_for(n_agg, 4), 128, 4 * sizeof(gather_ws), s>>>(ctx->d_records, d_members, d_off, d_bits, bits_stride, n_agg, nullptr,
                                                                                     nullptr, ctx->n_val, ctx->d_guard, d_checksum_out);
     } else {
-        k_g1_gather_ldg_probe<<<blocks_for(n_agg, 4), 128, 0, s>>>(ctx->d_records, d_members, d_off, d_bits, bits_stride, n_agg, ctx->n_val, d_checksum_out);
+        k_g1_gather_ldg_probe<<<n_agg, 128, 0, s>>>(ctx->d_records, d_members, d_off, d_bits, bits_stride, n_agg, ctx->n_val, d_checksum_out);
     }
     CKL(ctx);
     return B2_OK;
@@ -433,23 +484,33 @@ int b2_gather_probe_dev(b2_ctx* ctx, const uint32_t* d_members, const uint32_t* 
 // ------------------------------------------------------------------------------------------ bls.Aggregate
 // front: stage 1 + 2 (decompress every signature, per-segment Jacobian sums into V.sumjac);  finish: stage 3 (one
 // inversion per segment -> compressed bytes; with `handoff` also the affine point + subgroup-checked flag for verify_main).
+// `seg_stream`: the stream the per-segment sums run on.  Same as `s` for the synchronous entry points.  Under the epoch pipeline it
+// is the slot's TAIL stream: the decompressed points then live in the slot's own buffer and the caller's stream goes straight on to
+// the next epoch's decompression instead of waiting ~2 ms for a 2 048-warp kernel that cannot fill the chip.
 static int aggregate_front(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig,
-                           int32_t* d_seg_status, cudaStream_t s, int reserve_slot = -1) {
+                           int32_t* d_seg_status, cudaStream_t s, int reserve_slot = -1, bool own_buffers = false) {
     int rc;
-    if ((rc = ensure(ctx, ctx->sc_g2aff, (size_t)n_sig * 192 + 16)) || (rc = ensure(ctx, ctx->sc_g2st, n_sig + 16)) ||
-        (rc = ensure(ctx, V.sumjac, (size_t)n_seg * 288)))
-        return rc;
+    dbuf& aff = own_buffers ? V.g2aff : ctx->sc_g2aff;
+    dbuf& st = own_buffers ? V.g2st : ctx->sc_g2st;
+    if ((rc = ensure(ctx, aff, (size_t)n_sig * 192 + 16)) || (rc = ensure(ctx, st, n_sig + 16)) || (rc = ensure(ctx, V.sumjac, (size_t)n_seg * 288))) return rc;
     if (n_sig && reserve_slot >= 0 && ctx->reserve_sms > 0 && n_sig >= (uint64_t)ctx->n_sm * 512) {
         unsigned long long* ctr = ctx->d_dec_counter + reserve_slot;
         CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
-        k_g2_decompress_persistent<<<ctx->n_sm * 4, 128, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p, ctr, ctx->reserved);
+        k_g2_decompress_persistent<<<ctx->n_sm * 4, 128, 0, s>>>(d_sig96, n_sig, (uint32_t*)aff.p, (uint8_t*)st.p, ctr, ctx->reserved);
         CKL(ctx);
     } else if (n_sig) {
-        k_g2_decompress<<<blocks_for(n_sig, ctx->dec_block), ctx->dec_block, 0, s>>>(d_sig96, n_sig, (uint32_t*)ctx->sc_g2aff.p, (uint8_t*)ctx->sc_g2st.p);
+        k_g2_decompress<<<blocks_for(n_sig, ctx->dec_block), ctx->dec_block, ctx->pow_smem ? 384 * ctx->dec_block : 0, s>>>(
+            d_sig96, n_sig, (uint32_t*)aff.p, (uint8_t*)st.p, ctx->pow_smem ? 1 : 0);
         CKL(ctx);
     }
-    k_g2_segment_sum<<<n_seg, 32, 0, s>>>((const uint32_t*)ctx->sc_g2aff.p, (const uint8_t*)ctx->sc_g2st.p, d_seg_off, n_seg,
-                                           (uint32_t*)V.sumjac.p, d_seg_status, n_sig, ctx->d_guard);
+    if (own_buffers) return B2_OK;          // the segment sums follow on the tail stream (aggregate_segments)
+    k_g2_segment_sum<<<n_seg, 32, 0, s>>>((const uint32_t*)aff.p, (const uint8_t*)st.p, d_seg_off, n_seg, (uint32_t*)V.sumjac.p, d_seg_status, n_sig, ctx->d_guard);
+    CKL(ctx);
+    return B2_OK;
+}
+static int aggregate_segments(b2_ctx* ctx, vslot& V, const uint32_t* d_seg_off, uint32_t n_seg, uint64_t n_sig, int32_t* d_seg_status, cudaStream_t t) {
+    k_g2_segment_sum<<<n_seg, 32, 0, t>>>((const uint32_t*)V.g2aff.p, (const uint8_t*)V.g2st.p, d_seg_off, n_seg, (uint32_t*)V.sumjac.p, d_seg_status, n_sig,
+                                           ctx->d_guard);
     CKL(ctx);
     return B2_OK;
 }
@@ -653,22 +714,29 @@ int b2_fast_aggregate_verify_dev(b2_ctx* ctx, const uint32_t* d_members, const u
 //                bound work on few SMs; on `tail_stream` (the caller's own stream, or the context's tail stream so that
 //                it overlaps with the next epoch's epoch_start in the other slot).
 static int epoch_start(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
-                       uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, cudaStream_t s, bool team) {
+                       uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, cudaStream_t s, bool team,
+                       bool own_buffers = false) {
     vslot& V = ctx->slot[slot];
     int rc;
     CK(cudaStreamWaitEvent(s, V.ev_tail_done, 0));      // the slot's previous user (B2_EPOCH_SLOTS-or-fewer epochs ago) must have drained
     pk_source P = {d_members, d_off, d_bits, bits_stride, nullptr, 0};
     if ((rc = verify_fork(ctx, V, P, d_msg32, n_agg, s, team))) return rc;
-    if ((rc = aggregate_front(ctx, V, d_sig96, d_off, n_agg, n_sig, d_agg_status, s, team ? -1 : slot))) return rc;
+    V.segsum_pending = own_buffers;
+    V.n_sig_tail = n_sig;
+    if ((rc = aggregate_front(ctx, V, d_sig96, d_off, n_agg, n_sig, d_agg_status, s, team ? -1 : slot, own_buffers))) return rc;
     CK(cudaEventRecord(V.ev_seg, s));
     return B2_OK;
 }
 static int epoch_tail(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
-                      const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
+                      const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, int32_t* d_agg_status,
                       uint8_t* d_ok_out, cudaStream_t t, bool team) {
     vslot& V = ctx->slot[slot];
     int rc;
     CK(cudaStreamWaitEvent(t, V.ev_seg, 0));
+    if (V.segsum_pending) {
+        if ((rc = aggregate_segments(ctx, V, d_off, n_agg, V.n_sig_tail, d_agg_status, t))) return rc;
+        V.segsum_pending = false;
+    }
     if ((rc = aggregate_finish(ctx, V, n_agg, d_agg_sig96, d_agg_status, true, t, team ? 32u : ctx->tail_block))) return rc;
     if ((rc = verify_main(ctx, V, nullptr, n_agg, d_ok_out, t, team))) return rc;
     if (d_target_epoch) {
@@ -706,10 +774,10 @@ int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint
     REQUIRE(ctx->n_val > 0, "epoch_start_dev: registry not loaded");
     CK(cudaSetDevice(ctx->device));
     return epoch_start(ctx, slot, d_sig96, d_members, d_off, d_bits, bits_stride, d_msg32, n_agg, n_sig, d_agg_status, (cudaStream_t)stream,
-                       ctx->epoch_team);
+                       ctx->epoch_team, ctx->segsum_tail);
 }
 int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
-                      const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, const int32_t* d_agg_status,
+                      const uint64_t* d_target_epoch, const uint32_t* d_block_idx, uint32_t n_agg, uint8_t* d_agg_sig96, int32_t* d_agg_status,
                       uint8_t* d_ok_out) {
     B2_NVTX;
     REQUIRE(ctx && slot >= 0 && slot < B2_EPOCH_SLOTS && d_members && d_off && d_bits && (!d_target_epoch == !d_block_idx) && d_agg_sig96 && d_agg_status && d_ok_out &&
@@ -1267,6 +1335,7 @@ int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t jus
     A.boost_score = boost_score;
     size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8 + 8;
     A.use_smem = smem <= 226 * 1024 && A.n <= 15 * 1024;   // 227 KB per block minus the kernel's static shared memory
+    A.dbg = ctx->d_dbg;
     k_ghost_tree<<<1, 1024, A.use_smem ? smem : 0, s>>>(A);
     CKL(ctx);
     return B2_OK;
@@ -1285,12 +1354,74 @@ int b2_get_weights(b2_ctx* ctx, int32_t boost_idx, uint64_t boost_score, uint64_
     return B2_OK;
 }
 
+static void fill_tree_args(b2_ctx* ctx, ghost_tree_args& A, uint64_t* d_votes_preorder, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
+                           uint64_t* d_weight_out, uint32_t* d_head_idx_out) {
+    A.n = ctx->n_blocks;
+    A.pre = ctx->d_pre;
+    A.inv = ctx->d_inv;
+    A.size_keep = ctx->d_size_keep;
+    A.rank = ctx->d_rank;
+    A.votes = (unsigned long long*)d_votes_preorder;
+    A.g_w = ctx->d_prefix;
+    A.g_w2 = ctx->d_w2;
+    A.g_size = ctx->d_gsize;
+    A.g_next = ctx->d_next;
+    A.weight_out = (unsigned long long*)d_weight_out;
+    A.head_out = d_head_idx_out;
+    A.justified = justified_idx;
+    A.boost_idx = boost_idx;
+    A.boost_score = boost_score;
+    const size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8 + 8;
+    A.use_smem = smem <= 226 * 1024 && A.n <= 15 * 1024;   // 227 KB per block minus the kernel's static shared memory
+    A.dbg = ctx->d_dbg;
+}
+
+// Diagnostics: SM-clock stamps (clock64) of the phases of the LAST b2_get_head / b2_head_from_votes_dev of this context: out32[0..7] =
+// tree phase boundaries (start, staged, scanned, weights, weights stored, marked, counted, head found), out32[15] = tree end,
+// out32[16..19] = vote scatter of CTA 0 (start, bins zeroed, scattered, flushed).  For profiling (tools/, profiles/), not for results.
+int b2_debug_head_clocks(b2_ctx* ctx, uint64_t* out32) {
+    REQUIRE(ctx && out32, "debug_head_clocks: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out32, ctx->d_dbg, 32 * 8, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
 int b2_get_head(b2_ctx* ctx, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score, uint32_t* head_idx_out) {
     B2_NVTX;
     REQUIRE(ctx && head_idx_out, "get_head: bad arguments");
     REQUIRE(ctx->n_val > 0 && ctx->n_blocks > 0, "get_head: registry or tree not loaded");
+    REQUIRE(justified_idx < ctx->n_blocks && boost_idx < (int32_t)ctx->n_blocks, "get_head: block index out of range");
     int rc;
     cudaStream_t s = ctx->s_main;
+    ghost_tree_args A;
+    fill_tree_args(ctx, A, (uint64_t*)ctx->d_votes, justified_idx, boost_idx, boost_score, nullptr, ctx->d_head);
+    if (ctx->head_fused && A.use_smem) {
+        // one launch; the kernel writes (head, sequence) into mapped pinned memory and the host spins on the sequence number
+        CK(cudaSetDevice(ctx->device));
+        ghost_votes_args V = {ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff, ctx->fc_min_key, 1u,
+                              ctx->fc_exclude_slashed ? 3u : 1u};
+        const uint32_t seq = ++ctx->head_seq ? ctx->head_seq : ++ctx->head_seq;       // never 0
+        const size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8 + 8;
+        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->n_sm, (ctx->n_val + 1023) / 1024);
+        k_get_head_fused<<<grid, 1024, smem, s>>>(V, A, ctx->d_ticket, ctx->d_head_host, seq);
+        CKL(ctx);
+        CK(cudaEventRecord(ctx->ev_votes_done, s));
+        for (uint64_t spins = 0; ctx->h_head[1] != seq; spins++) {
+            if ((spins & 0xfffff) == 0xfffff) {                 // every ~1M polls: has the kernel died?
+                cudaError_t q = cudaStreamQuery(s);
+                if (q != cudaErrorNotReady && q != cudaSuccess) return fail_cuda(ctx, q, "get_head kernel");
+                if (q == cudaSuccess && ctx->h_head[1] != seq) {    // finished without publishing: should not happen; fall back to a copy
+                    uint32_t h = 0;
+                    CK(cudaMemcpy(&h, ctx->d_head, 4, cudaMemcpyDeviceToHost));
+                    *head_idx_out = h;
+                    return B2_OK;
+                }
+            }
+        }
+        *head_idx_out = ctx->h_head[0];
+        return B2_OK;
+    }
     if ((rc = b2_vote_weights_dev(ctx, (uint64_t*)ctx->d_votes, s))) return rc;
     if ((rc = b2_head_from_votes_dev(ctx, (uint64_t*)ctx->d_votes, justified_idx, boost_idx, boost_score, nullptr, ctx->d_head, s))) return rc;
     uint32_t h = 0;

@@ -249,12 +249,31 @@ HD void g1_compress(const g1_jac& p, uint8_t* out) {
 }
 
 // 96 bytes (x.c1 || x.c0) -> affine G2 point.  On-curve implied; subgroup NOT checked.
-HDN int g2_decompress(const uint8_t* in, g2_aff& out) {
-    uint8_t b0 = in[0];
+HDN int g2_decompress(const uint8_t* in, g2_aff& out, uint32_t* tab = nullptr, uint32_t tab_stride = 0) {
+    fp x1c, x0c;
+    uint8_t b0;
+#if defined(__CUDA_ARCH__) && !defined(B2_SIG_BYTE_LOADS)
+    if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+        // 96 contiguous bytes per signature: six 128-bit loads instead of 96 byte loads
+        uint32_t w[24];
+        const uint4* in4 = reinterpret_cast<const uint4*>(in);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const uint4 v = in4[k];
+            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+        b0 = (uint8_t)(w[0] & 0xffu);
+        x1c = fp_from_be48_words(w);
+        x0c = fp_from_be48_words(w + 12);
+    } else
+#endif
+    {
+        b0 = in[0];
+        x1c = fp_from_be48(in);
+        x0c = fp_from_be48(in + 48);
+    }
     if (!(b0 & 0x80)) return DEC_BAD;
-    fp x1c = fp_from_be48(in);
     x1c.l[11] &= 0x1fffffffu;
-    fp x0c = fp_from_be48(in + 48);
     if (b0 & 0x40) {
         if ((b0 & 0x20) || !fp_is_zero(x1c) || !fp_is_zero(x0c)) return DEC_BAD;
         return DEC_INF;
@@ -264,7 +283,7 @@ HDN int g2_decompress(const uint8_t* in, g2_aff& out) {
     x.c0 = fp_to_mont(x0c);
     x.c1 = fp_to_mont(x1c);
     fp2 y;
-    if (!fp2_sqrt(fp2_add(fp2_mul(fp2_sqr(x), x), fp2_load_const(C_B2)), y)) return DEC_BAD;
+    if (!fp2_sqrt(fp2_add(fp2_mul(fp2_sqr(x), x), fp2_load_const(C_B2)), y, tab, tab_stride)) return DEC_BAD;
     if (fp2_is_lex_large(y) != ((b0 & 0x20) != 0)) y = fp2_neg(y);
     out.x = x;
     out.y = y;

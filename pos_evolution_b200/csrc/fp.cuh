@@ -316,31 +316,66 @@ HD fp fp_mul8(const fp& a) { return fp_dbl(fp_mul4(a)); }
 // word 0 = number of steps, then (n_squarings << 8 | table index), index 255 = squarings only; window 4, table of the
 // eight odd powers a^1..a^15).  The schedule is the same in every thread, so nothing diverges.  For (p-3)/4 this is
 // 379 squarings + 76 multiplications + 8 for the table (the fixed-window version needed 380 + 92 + 14).
-HDN fp fp_pow_prog(const fp& a, int off) {
+// Where the eight odd powers live.  pow_tbl_local: a per-thread array -- dynamically indexed, so the compiler puts it in LOCAL memory
+// (384 B per thread; with 16 resident warps per SM these tables overflow L1 and their evicted lines are what made k_g2_decompress
+// write 1.2 GB to DRAM per launch, profiles/r1c_g2_decompress_raw.csv).  pow_tbl_strided: caller-provided SHARED memory, word (i, limb) of
+// thread t at base[(12 i + limb) * stride + t]: conflict-free, never leaves the SM.
+struct pow_tbl_local {
+    fp t[8];
+    HD void set(int i, const fp& v) { t[i] = v; }
+    HD fp get(uint32_t i) const { return t[i]; }
+};
+struct pow_tbl_strided {
+    uint32_t* base;
+    uint32_t stride;
+    HD void set(int i, const fp& v) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) base[(12 * i + k) * stride] = v.l[k];
+    }
+    HD fp get(uint32_t i) const {
+        fp r;
+#pragma unroll
+        for (int k = 0; k < 12; k++) r.l[k] = base[(12 * i + k) * stride];
+        return r;
+    }
+};
+template <class TBL> HDN fp fp_pow_prog_t(const fp& a, int off, TBL& tbl) {
     const uint32_t* prog = const_table() + off;
-    fp tbl[8];
     fp a2 = fp_sqr(a);
-    tbl[0] = a;
+    fp cur = a;
+    tbl.set(0, cur);
 #pragma unroll 1
-    for (int i = 1; i < 8; i++) tbl[i] = fp_mul(tbl[i - 1], a2);
+    for (int i = 1; i < 8; i++) {
+        cur = fp_mul(cur, a2);
+        tbl.set(i, cur);
+    }
     const uint32_t n = prog[0];
-    fp r = tbl[prog[1] & 0xffu];
+    fp r = tbl.get(prog[1] & 0xffu);
 #pragma unroll 1
     for (uint32_t k = 2; k <= n; k++) {
         const uint32_t op = prog[k];
 #pragma unroll 1
         for (uint32_t s = op >> 8; s; s--) r = fp_sqr(r);
         const uint32_t idx = op & 0xffu;
-        if (idx != 0xffu) r = fp_mul(r, tbl[idx]);
+        if (idx != 0xffu) r = fp_mul(r, tbl.get(idx));
     }
     return r;
+}
+// tab == nullptr: table in a per-thread array; else 96 words per thread in shared memory at tab[(12 i + limb) * tab_stride]
+HD fp fp_pow_prog(const fp& a, int off, uint32_t* tab = nullptr, uint32_t tab_stride = 0) {
+    if (tab) {
+        pow_tbl_strided t = {tab, tab_stride};
+        return fp_pow_prog_t(a, off, t);
+    }
+    pow_tbl_local t;
+    return fp_pow_prog_t(a, off, t);
 }
 
 HD fp fp_inv(const fp& a) { return fp_pow_prog(a, C_PROG_PM2); }        // 0 -> 0
 
 // d = a^((p-3)/4).  Then a*d = a^((p+1)/4) is the square-root candidate and, when a is a
 // non-zero square, d = 1/sqrt(a).
-HD fp fp_pow_pm3d4(const fp& a) { return fp_pow_prog(a, C_PROG_PM3D4); }
+HD fp fp_pow_pm3d4(const fp& a, uint32_t* tab = nullptr, uint32_t tab_stride = 0) { return fp_pow_prog(a, C_PROG_PM3D4, tab, tab_stride); }
 
 // sqrt in Fp: returns true and writes a root when `a` is a square
 HD bool fp_sqrt(const fp& a, fp& root) {
@@ -369,6 +404,16 @@ HD void fp_to_be48(const fp& canon, uint8_t* out) {
         out[4 * i + 2] = (uint8_t)(w >> 8);
         out[4 * i + 3] = (uint8_t)w;
     }
+}
+// the same from twelve 32-bit words loaded as they lie in memory (little-endian loads of big-endian bytes): one byte swap per limb
+HD fp fp_from_be48_words(const uint32_t* w) {
+    fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const uint32_t v = w[i];
+        r.l[11 - i] = (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+    }
+    return r;
 }
 HD fp fp_from_be48(const uint8_t* in) {
     fp r;

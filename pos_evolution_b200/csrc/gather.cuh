@@ -194,31 +194,51 @@ __global__ void __launch_bounds__(128) k_g1_gather_tma(const uint32_t* __restric
     }
 }
 
-// the same checksum with plain loads (one warp per aggregate, lane strides the members, six LDG.E.128 per record): the A/B
-// partner of the TMA probe and the cross-check that both fetch the same bytes
+// The same checksum with plain loads, in the fastest form tools/gather_bench.cu found on the B200 (profiles/r2_gather_microbench.jsonl:
+// 2.83 TB/s cold against 1.58 TB/s for the TMA form above and 2.34 TB/s for a lane-per-record LDG form): one 128-thread block per
+// aggregate, the u32 indices of a 512-member chunk staged in shared memory, then thread t reads 16-byte chunk (c % 6) of selected
+// record (c / 6) for c = t, t + 128, ...: six consecutive lanes cover one 96-byte record, so a warp instruction touches ~11 lines
+// instead of 32, and all 24 loads of a thread are in flight before the first is used.  A/B partner of the TMA probe and the
+// cross-check that both fetch the same bytes.
 __global__ void __launch_bounds__(128) k_g1_gather_ldg_probe(const uint32_t* __restrict__ records, const uint32_t* __restrict__ members,
                                                               const uint32_t* __restrict__ off, const uint8_t* __restrict__ bits, uint32_t bits_stride,
                                                               uint32_t n_agg, uint64_t n_val, uint32_t* probe_out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t a = blockIdx.x * (blockDim.x >> 5) + warp;
+    __shared__ uint32_t sel[B2_GATHER_CHUNK];          // registry indices of the SET members of the chunk, compacted
+    __shared__ uint32_t n_sel, part[4];
+    const uint32_t a = blockIdx.x, t = threadIdx.x;
     if (a >= n_agg) return;
     const uint32_t o0 = off[a], o1 = off[a + 1];
-    uint32_t size = (o1 < o0 || o1 - o0 > bits_stride * 8u) ? 0u : o1 - o0, chk = 0;
-#pragma unroll 2
-    for (uint32_t j = lane; j < size; j += 32) {
-        if (!((bits[(uint64_t)a * bits_stride + (j >> 3)] >> (j & 7)) & 1)) continue;
-        const uint32_t idx = members[o0 + j];
-        if (idx >= n_val) continue;
-        const uint4* r4 = reinterpret_cast<const uint4*>(records + 24 * (uint64_t)idx);
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const uint4 v = __ldg(r4 + k);
-            chk ^= v.x ^ v.y ^ v.z ^ v.w;
+    const uint32_t size = (o1 < o0 || o1 - o0 > bits_stride * 8u) ? 0u : o1 - o0;
+    uint32_t chk = 0;
+    for (uint32_t c0 = 0; c0 < size; c0 += B2_GATHER_CHUNK) {
+        const uint32_t cn = min((uint32_t)B2_GATHER_CHUNK, size - c0);
+        if (t == 0) n_sel = 0;
+        __syncthreads();
+        for (uint32_t j = t; j < cn; j += 128) {
+            const uint32_t m = c0 + j;
+            if ((bits[(uint64_t)a * bits_stride + (m >> 3)] >> (m & 7)) & 1) {
+                const uint32_t idx = members[o0 + m];
+                if (idx < n_val) sel[atomicAdd(&n_sel, 1u)] = idx;      // order is irrelevant to an XOR
+            }
         }
+        __syncthreads();
+        const uint32_t n_chunks = n_sel * 6;
+        const uint4* rec4 = reinterpret_cast<const uint4*>(records);
+        uint4 v[24];
+#pragma unroll
+        for (int q = 0; q < 24; q++) {
+            const uint32_t c = q * 128 + t;
+            v[q] = c < n_chunks ? __ldg(rec4 + 6ull * sel[c / 6] + (c % 6)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 24; q++) chk ^= v[q].x ^ v[q].y ^ v[q].z ^ v[q].w;
+        __syncthreads();
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) chk ^= __shfl_down_sync(0xffffffffu, chk, d);
-    if (lane == 0) probe_out[a] = chk;
+    if ((t & 31) == 0) part[t >> 5] = chk;
+    __syncthreads();
+    if (t == 0) probe_out[a] = part[0] ^ part[1] ^ part[2] ^ part[3];
 }
 
 }  // namespace b2

@@ -128,13 +128,16 @@ __global__ void __launch_bounds__(128) k_g1_segment_sum(const uint32_t* __restri
 
 // ------------------------------------------------------------------------------------------ K3: bls.Aggregate
 // stage 1: one thread per signature: ZCash decode + Fp2 square root (two Fp exponentiations) -> affine point
-__global__ void __launch_bounds__(128, 4) k_g2_decompress(const uint8_t* __restrict__ sig96, uint64_t n, uint32_t* aff_out, uint8_t* st_out) {
+// use_smem != 0: the sliding-window tables of the two exponentiations live in dynamic shared memory (96 words per thread, launch with
+// 384 B * blockDim.x) instead of local memory -- see pow_tbl_strided in fp.cuh
+__global__ void __launch_bounds__(128, 4) k_g2_decompress(const uint8_t* __restrict__ sig96, uint64_t n, uint32_t* aff_out, uint8_t* st_out, int use_smem) {
+    extern __shared__ uint32_t pow_tab[];
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2_aff s;
     s.x = fp2_zero();
     s.y = fp2_zero();
-    int st = g2_decompress(sig96 + 96 * i, s);
+    int st = g2_decompress(sig96 + 96 * i, s, use_smem ? pow_tab + threadIdx.x : nullptr, blockDim.x);
     uint4* o = reinterpret_cast<uint4*>(aff_out + 48 * i);
     const uint32_t* w = reinterpret_cast<const uint32_t*>(&s);
 #pragma unroll
@@ -516,51 +519,77 @@ __global__ void __launch_bounds__(256) k_ghost_votes(uint64_t n, const unsigned 
 // leader adds into the CTA's shared bins, and only non-zero bins are flushed to global memory -- one atomic per
 // (CTA, voted block) instead of one per (warp, voted block), which matters when a million validators agree on a
 // handful of recent blocks (the realistic case) and the global atomics would serialise on those addresses.
+__device__ __forceinline__ void ghost_votes_body(unsigned long long* bins, uint64_t n, const unsigned long long* __restrict__ lmd_key,
+                                                 const uint32_t* __restrict__ lmd_block, const uint8_t* __restrict__ equiv,
+                                                 const uint8_t* __restrict__ flags, const uint64_t* __restrict__ eff,
+                                                 const uint32_t* __restrict__ pre, uint32_t n_blocks, unsigned long long* votes, unsigned long long min_key, uint32_t flag_need, uint32_t flag_mask,
+                                                 unsigned long long* dbg = nullptr) {
+#define B2_VOTE_STAMP(k) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[k] = clock64(); } while (0)
+    B2_VOTE_STAMP(16);
+    for (uint32_t i = threadIdx.x; i < n_blocks; i += blockDim.x) bins[i] = 0;
+    __syncthreads();
+    B2_VOTE_STAMP(17);
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + stride - 1) / stride * stride;            // whole warps stay converged for the shuffles
+    // Four validators per thread and trip: all twenty table loads (key, block, balance, flags, equivocation byte -- addresses depend on
+    // the validator index only) are issued before the first is used, then the one dependent gather (block -> pre-order position, a
+    // 40 KB table that lives in L1).  The round-1 form tested `key != 0 && ...` load by load, i.e. four dependent round trips per
+    // validator (ncu: 72 % of the samples in stall_long_sb at those four points, profiles/r2_ghost_source_summary.txt).
+    constexpr int U = 4;
+    for (uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < n_round; v0 += U * stride) {
+        unsigned long long key[U], bal[U];
+        uint32_t blk[U], fl[U], eq[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t v = v0 + u * stride;
+            const bool in = v < n;
+            key[u] = in ? lmd_key[v] : 0ull;
+            blk[u] = in ? lmd_block[v] : 0u;
+            bal[u] = in ? eff[v] : 0ull;
+            fl[u] = in ? flags[v] : 0u;
+            eq[u] = in ? equiv[v] : 1u;
+        }
+        uint32_t b[U];
+        bool on[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            on[u] = key[u] != 0 && key[u] >= min_key && !eq[u] && ((fl[u] & flag_mask) == flag_need) && blk[u] < n_blocks;
+            b[u] = on[u] ? pre[blk[u]] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (v0 + u * stride >= n_round) break;                          // warp-uniform
+            // fast path: the whole warp votes for one block (the common case on a healthy chain): one shuffle reduction, one
+            // shared-memory atomic.  Otherwise every lane adds into the CTA-private bins itself (shared-memory atomics).
+            const unsigned voting = __ballot_sync(B2_FULL_MASK, on[u]);
+            if (voting == 0) continue;
+            const uint32_t b0 = __shfl_sync(B2_FULL_MASK, b[u], __ffs(voting) - 1);
+            const bool uniform = __all_sync(B2_FULL_MASK, !on[u] || b[u] == b0);
+            if (uniform) {
+                unsigned long long sum = on[u] ? bal[u] : 0ull;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) sum += __shfl_down_sync(B2_FULL_MASK, sum, d);
+                if (lane == 0) atomicAdd(&bins[b0], sum);
+            } else if (on[u]) {
+                atomicAdd(&bins[b[u]], bal[u]);
+            }
+        }
+    }
+    __syncthreads();
+    B2_VOTE_STAMP(18);
+    for (uint32_t i = threadIdx.x; i < n_blocks; i += blockDim.x) {
+        unsigned long long w = bins[i];
+        if (w) atomicAdd(&votes[i], w);
+    }
+    B2_VOTE_STAMP(19);
+}
 __global__ void __launch_bounds__(1024) k_ghost_votes_smem(uint64_t n, const unsigned long long* __restrict__ lmd_key,
                                                             const uint32_t* __restrict__ lmd_block, const uint8_t* __restrict__ equiv,
                                                             const uint8_t* __restrict__ flags, const uint64_t* __restrict__ eff,
                                                             const uint32_t* __restrict__ pre, uint32_t n_blocks, unsigned long long* votes, unsigned long long min_key, uint32_t flag_need, uint32_t flag_mask) {
     extern __shared__ unsigned long long bins[];
-    for (uint32_t i = threadIdx.x; i < n_blocks; i += blockDim.x) bins[i] = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_round = (n + stride - 1) / stride * stride;            // whole warps stay converged for the shuffles
-    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_round; v += stride) {
-        bool on = v < n;
-        uint32_t b = 0xffffffffu;
-        unsigned long long bal = 0;
-        if (on) {
-            on = lmd_key[v] != 0 && lmd_key[v] >= min_key && !equiv[v] && ((flags[v] & flag_mask) == flag_need);
-            if (on) {
-                uint32_t blk = lmd_block[v];
-                on = blk < n_blocks;
-                if (on) {
-                    b = pre[blk];
-                    bal = eff[v];
-                }
-            }
-        }
-        // fast path: the whole warp votes for one block (the common case on a healthy chain): one shuffle reduction, one
-        // shared-memory atomic.  Otherwise every lane adds into the CTA-private bins itself (shared-memory atomics).
-        const unsigned voting = __ballot_sync(B2_FULL_MASK, on);
-        if (voting == 0) continue;
-        const uint32_t b0 = __shfl_sync(B2_FULL_MASK, b, __ffs(voting) - 1);
-        const bool uniform = __all_sync(B2_FULL_MASK, !on || b == b0);
-        if (uniform) {
-            unsigned long long sum = bal;
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) sum += __shfl_down_sync(B2_FULL_MASK, sum, d);
-            if (lane == 0) atomicAdd(&bins[b0], sum);
-        } else if (on) {
-            atomicAdd(&bins[b], bal);
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n_blocks; i += blockDim.x) {
-        unsigned long long w = bins[i];
-        if (w) atomicAdd(&votes[i], w);
-    }
+    ghost_votes_body(bins, n, lmd_key, lmd_block, equiv, flags, eff, pre, n_blocks, votes, min_key, flag_need, flag_mask);
 }
 
 // ------------------------------------------------------------------------------------------ K9: subtree weights + head
@@ -591,6 +620,7 @@ struct ghost_tree_args {
     int32_t boost_idx;
     unsigned long long boost_score;
     int use_smem;
+    unsigned long long* dbg;     // optional: thread 0 of the tree phase stores clock64() at its phase boundaries (b2_debug_head_clocks)
 };
 
 // exclusive prefix sum of x[0..n) in place, x[n] = total; every thread of the block must call it
@@ -630,12 +660,13 @@ template <class T> __device__ __forceinline__ void block_exclusive_scan(T* x, ui
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
-    extern __shared__ unsigned long long smem_u64[];
+__device__ __forceinline__ void ghost_tree_body(const ghost_tree_args& A, unsigned long long* smem_u64, uint32_t* host_out, uint32_t host_seq) {
     __shared__ unsigned long long warp_tot[32];
     __shared__ uint32_t warp_tot32[32];
     __shared__ uint32_t head_pos;
     const uint32_t n = A.n, tid = threadIdx.x, T = blockDim.x;
+#define B2_TREE_STAMP(k) do { if (A.dbg && tid == 0) A.dbg[k] = clock64(); } while (0)
+    B2_TREE_STAMP(0);
     unsigned long long* W = A.use_smem ? smem_u64 : A.g_w;                                     // n+1: votes -> prefix -> weights
     uint32_t* size = A.use_smem ? reinterpret_cast<uint32_t*>(smem_u64 + (n + 1)) : A.g_size;   // n
     uint32_t* mark = A.use_smem ? size + n : A.g_next;                                          // n+1: marks -> counts
@@ -643,7 +674,7 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
     if (tid == 0) head_pos = 0;
     // stage votes (+ boost) and sizes, coalesced; leave the global accumulator clean for the next call
     for (uint32_t p = tid; p < n; p += T) {
-        unsigned long long v = A.votes[p];
+        unsigned long long v = __ldcg(&A.votes[p]);      // L2: in the fused kernel other CTAs' atomics produced these values
         A.votes[p] = 0;
         if (p == boost_p) v += A.boost_score;
         W[p] = v;
@@ -652,7 +683,9 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
     }
     if (tid == 0) mark[n] = 0;
     __syncthreads();
+    B2_TREE_STAMP(1);
     block_exclusive_scan(W, n, warp_tot);
+    B2_TREE_STAMP(2);
     // weights: w[p] = S[p + size] - S[p].  Shared-memory mode overwrites S in place (through registers: the smem budget
     // caps n at ~14 500 = 15 per thread); global mode writes a separate array.
     unsigned long long* Wt = A.use_smem ? W : A.g_w2;
@@ -665,6 +698,7 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
             if (p < n) wreg[j] = W[p + (size[p] & 0x7fffffffu)] - W[p];
         }
         __syncthreads();
+    B2_TREE_STAMP(3);
 #pragma unroll
         for (int j = 0; j < MAXPT; j++) {
             uint32_t p = tid + j * T;
@@ -674,6 +708,7 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
         for (uint32_t p = tid; p < n; p += T) Wt[p] = W[p + (size[p] & 0x7fffffffu)] - W[p];
     }
     __syncthreads();
+    B2_TREE_STAMP(4);
     if (A.weight_out)
         for (uint32_t b = tid; b < n; b += T) A.weight_out[b] = Wt[A.pre[b]];
     // every child that is not its parent's best child gets +1 at its position and -1 just past its subtree
@@ -701,7 +736,9 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
             }
     }
     __syncthreads();
+    B2_TREE_STAMP(5);
     block_exclusive_scan(mark, n, warp_tot32);          // mark[p] = number of marked proper ancestors ... of positions < p
+    B2_TREE_STAMP(6);
     // after the scan mark[p+1] is the inclusive count at p = number of marked blocks among p and its ancestors.  The head path
     // below the justified block = the positions of its subtree whose count equals the justified block's own count
     // (nothing marked in between); the head is the last of them in pre-order.
@@ -717,7 +754,48 @@ __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
     }
     if (have) atomicMax(&head_pos, best_pos);
     __syncthreads();
-    if (tid == 0) *A.head_out = (A.justified < n) ? A.inv[max(head_pos, jp)] : 0xffffffffu;
+    B2_TREE_STAMP(7);
+    if (tid == 0) {
+        const uint32_t h = (A.justified < n) ? A.inv[max(head_pos, jp)] : 0xffffffffu;
+        *A.head_out = h;
+        if (host_out) {                         // zero-copy result: mapped pinned host memory, head first, then the sequence number
+            reinterpret_cast<volatile uint32_t*>(host_out)[0] = h;
+            __threadfence_system();
+            reinterpret_cast<volatile uint32_t*>(host_out)[1] = host_seq;
+        }
+    }
+    B2_TREE_STAMP(15);
+}
+__global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
+    extern __shared__ unsigned long long smem_u64[];
+    ghost_tree_body(A, smem_u64, nullptr, 0);
+}
+// get_head in ONE launch (b2_get_head): every CTA scatters its share of the votes (K8), the CTA that finishes last -- elected by a
+// ticket counter -- runs the tree phase (K9) on the completed vote array and writes the head straight into mapped pinned host memory
+// (head, then a sequence number the host spins on): no second launch, no device-to-host copy, no stream synchronisation.
+struct ghost_votes_args {
+    uint64_t n;
+    const unsigned long long* lmd_key;
+    const uint32_t* lmd_block;
+    const uint8_t *equiv, *flags;
+    const uint64_t* eff;
+    unsigned long long min_key;
+    uint32_t flag_need, flag_mask;
+};
+__global__ void __launch_bounds__(1024) k_get_head_fused(ghost_votes_args V, ghost_tree_args A, unsigned int* ticket, uint32_t* host_out, uint32_t host_seq) {
+    extern __shared__ unsigned long long smem_u64[];
+    __shared__ bool is_last;
+    ghost_votes_body(smem_u64, V.n, V.lmd_key, V.lmd_block, V.equiv, V.flags, V.eff, A.pre, A.n, A.votes, V.min_key, V.flag_need, V.flag_mask, A.dbg);
+    __syncthreads();                                   // every flush atomic of this CTA has been issued
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();                                   // the other CTAs' vote atomics are visible (they live in L2)
+    if (threadIdx.x == 0) *ticket = 0;                 // re-armed for the next call
+    ghost_tree_body(A, smem_u64, host_out, host_seq);
 }
 
 }  // namespace b2

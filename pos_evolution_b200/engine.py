@@ -69,6 +69,13 @@ class Engine:
         self.n_validators = n
         return valid
 
+    def key_validate(self, pubkeys48):
+        """bls.KeyValidate for explicit pubkeys (uint8[n,48]) -> uint8[n]; the registry on the device is not touched."""
+        pk = _c(pubkeys48, np.uint8).reshape(-1, 48)
+        out = np.zeros(pk.shape[0], dtype=np.uint8)
+        self._ck(self.lib.b2_key_validate(self.h, _p(pk), pk.shape[0], _p(out)))
+        return out
+
     def registry_update_balances(self, effective_balance, flags):
         eff, fl = _c(effective_balance, np.uint64), _c(flags, np.uint8)
         self._ck(self.lib.b2_registry_update_balances(self.h, _p(eff), _p(fl), eff.shape[0]))
@@ -272,6 +279,12 @@ class Engine:
         out = ctypes.c_uint32(0)
         self._ck(self.lib.b2_get_head(self.h, int(justified_idx), int(boost_idx), int(boost_score), ctypes.byref(out)))
         return int(out.value)
+
+    def debug_head_clocks(self):
+        """clock64 stamps of the phases of the last get_head (profiling aid) -> uint64[32]"""
+        out = np.zeros(32, dtype=np.uint64)
+        self._ck(self.lib.b2_debug_head_clocks(self.h, _p(out)))
+        return out
 
     # ------------------------------------------------------------------ device-pointer entry points (torch CUDA tensors)
     @staticmethod

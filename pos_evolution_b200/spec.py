@@ -244,8 +244,16 @@ class Spec:
     def __init__(self, preset: Preset = MAINNET, engine: Engine = None):
         self.p = preset
         self.engine = engine if engine is not None else Engine(0)
-        self._registry_key = None
+        self._registry_key = None          # (length, fingerprint of the pubkey bytes) of the registry on the device
+        self._balances_key = None          # (state object, slot) whose effective balances / flags are on the device
+        self._balances_state = None
         self._committee_cache = {}
+        self._mirror = None                # device mirror of a Store (block tree + latest messages), see _sync_store
+        self.registry_valid = None         # KeyValidate verdict per validator of the registry on the device (uint8[n])
+        self.stats = {"registry_uploads": 0, "balance_refreshes": 0, "store_uploads": 0, "lmd_device_updates": 0}
+        # full: fingerprint = hash of ALL pubkeys on every call (O(n) host work, catches any in-place replacement);
+        # sampled: first / last / 62 strided pubkeys (O(1)); auto: full up to 65 536 validators, sampled above
+        self.registry_check = "auto"
 
     # ------------------------------------------------------------------ epochs / registry
     def compute_epoch_at_slot(self, slot):
@@ -275,6 +283,14 @@ class Spec:
 
     def get_total_balance(self, state, indices):                             # described at :811
         return max(self.p.EFFECTIVE_BALANCE_INCREMENT, sum(state.validators[i].effective_balance for i in indices))
+
+    @staticmethod
+    def has_flag(flags: int, flag_index: int) -> bool:                          # ParticipationFlags helper used at :747
+        return (int(flags) >> flag_index) & 1 == 1
+
+    @staticmethod
+    def add_flag(flags: int, flag_index: int) -> int:                           # :748
+        return int(flags) | (1 << flag_index)
 
     def get_unslashed_participating_indices(self, state, flag_index, epoch):   # described at :805-807 (host set form)
         cur = self.get_current_epoch(state)
@@ -426,24 +442,64 @@ class Spec:
         return out
 
     # ------------------------------------------------------------------ registry on the device
+    def _pubkey_fingerprint(self, validators):
+        n = len(validators)
+        mode = self.registry_check
+        if mode == "auto":
+            mode = "full" if n <= 65536 else "sampled"
+        h = hashlib.blake2b(digest_size=16)
+        if mode == "full":
+            h.update(b"".join(bytes(v.pubkey) for v in validators))
+        else:
+            step = max(1, n // 62)
+            for i in list(range(0, n, step)) + [n - 1]:
+                h.update(i.to_bytes(8, "little") + bytes(validators[i].pubkey))
+        return h.digest()
+
+    def invalidate_registry(self):
+        """Forget what is on the device: the next call re-uploads the registry and the store (call it after replacing pubkeys in
+        place in a registry larger than 65 536 validators, where the content check is sampled -- see registry_check)."""
+        self._registry_key = self._balances_key = self._balances_state = self._mirror = None
+
+    def sync_pubkeys(self, state):
+        """state.validators[*].pubkey on the device.  Decompressed + KeyValidated on the GPU ONCE per registry CONTENT: the cache key is
+        (length, fingerprint of the pubkey bytes), never an address -- so neither a recycled id() nor an in-place replacement can
+        alias a stale registry, and two states that share the same validator set (the justified state and a target checkpoint
+        state) share one upload.  Signature verification needs nothing else.  Returns True when it uploaded."""
+        validators = state.validators
+        n = len(validators)
+        key = (n, self._pubkey_fingerprint(validators))
+        if key == self._registry_key:
+            return False
+        pk = np.frombuffer(b"".join(bytes(v.pubkey) for v in validators), dtype=np.uint8).reshape(n, 48)
+        zero = np.zeros(n, dtype=np.uint64)
+        self.registry_valid = self.engine.registry_load(pk, zero, np.zeros(n, dtype=np.uint8))    # resets the device LMD table too
+        self._registry_key = key
+        self._balances_key = self._balances_state = self._mirror = None
+        self.stats["registry_uploads"] += 1
+        return True
+
     def sync_registry(self, state):
-        """Upload state.validators once (pubkeys decompressed + KeyValidated on the GPU); later calls only
-        refresh balances/flags when the same validator list is seen again."""
-        key = (id(state.validators), len(state.validators))
-        n = len(state.validators)
+        """sync_pubkeys + the per-validator effective balance / activity / slashed table of THIS state (what the fork-choice weights
+        and the FFG sums read).  Refreshed once per (state object, slot): the spec changes these fields only at epoch processing
+        (:122-133) and in slashings; a different state (or slot) re-reads them (an O(n) pass over the Python objects)."""
+        self.sync_pubkeys(state)
+        bkey = (id(state), state.slot)
+        if bkey == self._balances_key and state is self._balances_state:
+            return
+        validators = state.validators
+        n = len(validators)
         epoch = self.get_current_epoch(state)
-        eff = np.fromiter((v.effective_balance for v in state.validators), dtype=np.uint64, count=n)
+        eff = np.fromiter((v.effective_balance for v in validators), dtype=np.uint64, count=n)
         prev = self.get_previous_epoch(state)
         # bit0 active in the current epoch, bit1 slashed, bit2 active in the previous epoch (the FFG sums need both epochs)
         flags = np.fromiter(((1 if v.activation_epoch <= epoch < v.exit_epoch else 0) | (2 if v.slashed else 0)
                              | (4 if v.activation_epoch <= prev < v.exit_epoch else 0)
-                             for v in state.validators), dtype=np.uint8, count=n)
-        if key != self._registry_key:
-            pk = np.frombuffer(b"".join(bytes(v.pubkey) for v in state.validators), dtype=np.uint8).reshape(n, 48)
-            self.engine.registry_load(pk, eff, flags)
-            self._registry_key = key
-        else:
-            self.engine.registry_update_balances(eff, flags)
+                             for v in validators), dtype=np.uint8, count=n)
+        self.engine.registry_update_balances(eff, flags)
+        self.stats["balance_refreshes"] += 1
+        self._balances_key, self._balances_state = bkey, state                  # the state is held: its id() cannot be recycled
+        self._total_active = (int(eff[(flags & 1) != 0].astype(object).sum()) if n else 0, int(np.count_nonzero(flags & 1)))
 
     # ------------------------------------------------------------------ indexed attestations (called at :736, :745, :975-976)
     def get_attesting_indices(self, state, data, bits):
@@ -461,7 +517,7 @@ class Spec:
         """Batched is_valid_indexed_attestation: one GPU FastAggregateVerify call for the whole list."""
         if not indexed_list:
             return np.zeros(0, dtype=np.uint8)
-        self.sync_registry(state)
+        self.sync_pubkeys(state)
         n = len(state.validators)
         members, off, sigs, structurally_ok, data128, domains = [], [0], [], [], [], []
         for ia in indexed_list:
@@ -568,6 +624,7 @@ class Spec:
         """Flag scatter + proposer-reward numerators of :745-752 for a prefix of valid attestations on the GPU (order-exact),
         then the per-attestation integer division and the proposer credit of :752-754 on the host."""
         eng = self.engine
+        self.sync_registry(state)              # the reward numerators read THIS state's effective balances on the device
         cur = self.get_current_epoch(state)
         tables = (state.current_epoch_participation, state.previous_epoch_participation)
         per_inc = self.get_base_reward_per_increment(state)
@@ -591,15 +648,60 @@ class Spec:
                 state.balances[proposer] += int(v) // denominator
 
     # ------------------------------------------------------------------ fork choice
-    def update_latest_messages(self, store, attesting_indices, attestation):   # :1435-1441 (host dict form)
+    def update_latest_messages(self, store, attesting_indices, attestation):   # :1435-1441
+        """The store's dict is updated as the reference does; when the store is mirrored on the device (after a get_head /
+        get_weight call) the same update is applied to the device table by K7 (b2_latest_messages_update), so the next get_head
+        is a kernel launch, not a re-upload."""
         target, root = attestation.data.target, attestation.data.beacon_block_root
-        for i in attesting_indices:
+        indices = [int(i) for i in attesting_indices]
+        for i in indices:
             if i in store.equivocating_indices:
                 continue
             if i not in store.latest_messages or target.epoch > store.latest_messages[i].epoch:
                 store.latest_messages[i] = LatestMessage(epoch=target.epoch, root=root)
+        m = self._mirror
+        if m is not None and m["store"] is store:
+            blk = m["index"].get(root)
+            if blk is None or not indices or max(indices) >= m["n_val"] or target.epoch >= 0xFFFFFFFF:
+                self._mirror = None                  # a vote the device form cannot hold: fall back to a full re-upload
+            else:
+                k = len(indices)
+                bits = np.full((1, (k + 7) // 8), 0xFF, dtype=np.uint8)
+                if k & 7:
+                    bits[0, -1] = (1 << (k & 7)) - 1
+                self.engine.latest_messages_update(np.asarray(indices, dtype=np.uint32), [0, k], bits, [target.epoch], [blk])
+                m["n_msgs"] = len(store.latest_messages)
+                self.stats["lmd_device_updates"] += 1
+
+    def get_current_slot(self, store):
+        return (store.time - store.genesis_time) // getattr(self.p, "SECONDS_PER_SLOT", 12)
+
+    def get_ancestor(self, store, root, slot):
+        block = store.blocks[root]
+        while block.slot > slot:
+            root = block.parent_root
+            block = store.blocks[root]
+        return root
+
+    def validate_on_attestation(self, store, attestation, is_from_block):      # called at :970 (upstream fork-choice spec, v1.2.0)
+        target = attestation.data.target
+        if not is_from_block:                                                   # validate_target_epoch_against_current_time
+            current_epoch = self.compute_epoch_at_slot(self.get_current_slot(store))
+            previous_epoch = current_epoch - 1 if current_epoch > GENESIS_EPOCH else GENESIS_EPOCH
+            assert target.epoch in (current_epoch, previous_epoch)
+        assert target.epoch == self.compute_epoch_at_slot(attestation.data.slot)
+        assert target.root in store.blocks
+        assert attestation.data.beacon_block_root in store.blocks
+        assert store.blocks[attestation.data.beacon_block_root].slot <= attestation.data.slot
+        assert target.root == self.get_ancestor(store, attestation.data.beacon_block_root, self.compute_start_slot_at_epoch(target.epoch))
+        assert self.get_current_slot(store) >= attestation.data.slot + 1
 
     def on_attestation(self, store, attestation, is_from_block=False):         # :963-979 / :1423-1428
+        """AssertionError = invalid, as in the reference.  store_target_checkpoint_state (:971) needs process_slots, which is state
+        transition and out of scope: the target checkpoint state must already be in store.checkpoint_states
+        (the caller's on_block / on_tick put it there), otherwise the attestation is rejected."""
+        self.validate_on_attestation(store, attestation, is_from_block)
+        assert attestation.data.target in store.checkpoint_states, "target checkpoint state not in store (store_target_checkpoint_state is out of scope)"
         target_state = store.checkpoint_states[attestation.data.target]
         indexed = self.get_indexed_attestation(target_state, attestation)
         assert self.is_valid_indexed_attestation(target_state, indexed)
@@ -617,18 +719,27 @@ class Spec:
         state = store.block_states[store.justified_checkpoint.root]
         ok = self.are_valid_indexed_attestations(state, [a1, a2])              # both signatures in one GPU batch
         assert ok[0] and ok[1]
-        for index in set(a1.attesting_indices).intersection(a2.attesting_indices):
+        both = sorted(set(a1.attesting_indices).intersection(a2.attesting_indices))
+        for index in both:
             store.equivocating_indices.add(index)
+        m = self._mirror
+        if m is not None and m["store"] is store:
+            if hasattr(self.engine, "on_attester_slashing") and both and both[-1] < m["n_val"]:
+                self.engine.on_attester_slashing(both, both)                    # mark them on the device table as well
+                m["n_equiv"] = len(store.equivocating_indices)
+            else:
+                self._mirror = None
 
     def _store_arrays(self, store):
         """Store (dicts) -> the array form of include/b200pos.h: blocks below the justified root in topological order."""
+        import collections
         jroot = store.justified_checkpoint.root
         children = {}
         for r, b in store.blocks.items():
             children.setdefault(b.parent_root, []).append(r)
-        order, queue = [], [jroot]
+        order, queue = [], collections.deque([jroot])
         while queue:
-            r = queue.pop(0)
+            r = queue.popleft()
             order.append(r)
             queue.extend(children.get(r, []))
         index = {r: i for i, r in enumerate(order)}
@@ -650,30 +761,46 @@ class Spec:
         return order, index, parent, slot, roots, viable
 
     def _sync_store(self, store):
+        """Device mirror of the store: block tree (b2_tree_load) and latest messages (b2_latest_messages_load) are uploaded when the
+        store's SHAPE changed -- another store object, justified / finalized checkpoint moved, a block was added (on_block), the
+        registry changed, or latest_messages / equivocating_indices were changed behind this class's back (their sizes differ from
+        what the mirror recorded).  Votes that arrive through on_attestation / update_latest_messages are applied to the device
+        table incrementally, so between blocks get_head / get_weight cost one kernel sequence."""
         state = store.checkpoint_states[store.justified_checkpoint]
         self.sync_registry(state)
-        order, index, parent, slot, roots, viable = self._store_arrays(store)
-        self.engine.tree_load(parent, slot, roots, viable)
-        n = len(state.validators)
-        epoch = np.zeros(n, dtype=np.uint64)
-        blk = np.zeros(n, dtype=np.uint32)
-        has = np.zeros(n, dtype=np.uint8)
-        for v, lm in store.latest_messages.items():
-            if v < n and lm.root in index:
-                epoch[v], blk[v], has[v] = lm.epoch, index[lm.root], 1
-        eq = np.zeros(n, dtype=np.uint8)
-        for v in store.equivocating_indices:
-            if v < n:
-                eq[v] = 1
-        self.engine.latest_messages_load(epoch, blk, has, eq)
-        boost_idx, boost_score = -1, 0
-        if store.proposer_boost_root != ZERO32 and store.proposer_boost_root in index:
-            active = [v for v in state.validators if self.is_active_validator(v, self.get_current_epoch(state))]
-            num = len(active)
-            avg = self.get_total_active_balance(state) // num
-            boost_score = (num // self.p.SLOTS_PER_EPOCH) * avg * self.p.PROPOSER_SCORE_BOOST // 100
-            boost_idx = index[store.proposer_boost_root]
-        return order, index, boost_idx, boost_score
+        m = self._mirror
+        live = (m is not None and m["store"] is store and m["justified"] == store.justified_checkpoint and m["finalized"] == store.finalized_checkpoint
+                and m["n_blocks"] == len(store.blocks) and m["n_msgs"] == len(store.latest_messages) and m["n_equiv"] == len(store.equivocating_indices)
+                and m["n_val"] == len(state.validators))
+        if not live:
+            order, index, parent, slot, roots, viable = self._store_arrays(store)
+            self.engine.tree_load(parent, slot, roots, viable)
+            n = len(state.validators)
+            epoch = np.zeros(n, dtype=np.uint64)
+            blk = np.zeros(n, dtype=np.uint32)
+            has = np.zeros(n, dtype=np.uint8)
+            for v, lm in store.latest_messages.items():
+                if v < n and lm.root in index:
+                    epoch[v], blk[v], has[v] = lm.epoch, index[lm.root], 1
+            eq = np.zeros(n, dtype=np.uint8)
+            for v in store.equivocating_indices:
+                if v < n:
+                    eq[v] = 1
+            self.engine.latest_messages_load(epoch, blk, has, eq)
+            m = self._mirror = dict(store=store, justified=store.justified_checkpoint, finalized=store.finalized_checkpoint, n_blocks=len(store.blocks),
+                                    n_msgs=len(store.latest_messages), n_equiv=len(store.equivocating_indices), n_val=n, order=order, index=index,
+                                    boost=None)
+            self.stats["store_uploads"] += 1
+        bkey = (store.proposer_boost_root, self._balances_key)
+        if m["boost"] is None or m["boost"][0] != bkey:
+            boost_idx, boost_score = -1, 0
+            if store.proposer_boost_root != ZERO32 and store.proposer_boost_root in m["index"]:
+                total, num = self._total_active                                 # of the justified state, computed by sync_registry
+                avg = max(self.p.EFFECTIVE_BALANCE_INCREMENT, total) // num
+                boost_score = (num // self.p.SLOTS_PER_EPOCH) * avg * self.p.PROPOSER_SCORE_BOOST // 100
+                boost_idx = m["index"][store.proposer_boost_root]
+            m["boost"] = (bkey, boost_idx, boost_score)
+        return m["order"], m["index"], m["boost"][1], m["boost"][2]
 
     def get_latest_attesting_balance(self, store, root):                       # called at :1116 (v1.2.0 form)
         order, index, boost_idx, boost_score = self._sync_store(store)

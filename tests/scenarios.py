@@ -66,13 +66,14 @@ def minimal_state(n_validators: int = 64, slot: int = 9, preset=S.MINIMAL, pks=N
     return spec, state
 
 
-def make_attestation(spec, state, slot: int, index: int, bits=None, head_root=None, corrupt=None):
+def make_attestation(spec, state, slot: int, index: int, bits=None, head_root=None, corrupt=None, target_root=None):
     """A correctly-signed aggregate attestation for (slot, index); ``bits`` defaults to full participation."""
     committee = spec.get_beacon_committee(state, slot, index)
     bits = [True] * len(committee) if bits is None else list(bits)
     epoch = spec.compute_epoch_at_slot(slot)
     just = state.current_justified_checkpoint if epoch == spec.get_current_epoch(state) else state.previous_justified_checkpoint
-    target_root = spec.get_block_root(state, epoch) if spec.compute_start_slot_at_epoch(epoch) < state.slot else _h(b"t")
+    if target_root is None:
+        target_root = spec.get_block_root(state, epoch) if spec.compute_start_slot_at_epoch(epoch) < state.slot else _h(b"t")
     head = head_root if head_root is not None else spec.get_block_root_at_slot(state, slot)
     data = S.AttestationData(slot=slot, index=index, beacon_block_root=head, source=just,
                              target=S.Checkpoint(epoch, target_root))

@@ -143,16 +143,45 @@ def test_get_head_and_weight_match_oracle(env):
         assert pspec.get_head(pstore) == ospec.get_head(ostore)
         for b in (0, 1, n_blocks // 2, n_blocks - 1):
             assert pspec.get_weight(pstore, rb[b]) == ospec.get_latest_attesting_balance(ostore, rb[b])
-    # on_attestation: verify on the GPU, then the host LMD table moves exactly like the oracle's
-    att = scenarios.make_attestation(ospec, ostate2, 8, 0, head_root=rb[5])
+    # on_attestation: validate_on_attestation (store-consistent data only), verify on the GPU, then the host LMD table moves exactly
+    # like the oracle's AND the device mirror of the store moves with it (the next get_head needs no re-upload)
+    k = max(b for b in range(n_blocks) if slot[b] <= 8)
+    att = scenarios.make_attestation(ospec, ostate2, 8, 0, head_root=rb[k], target_root=rb[k])
     ostore.checkpoint_states[att.data.target] = ostate2
     pstore.checkpoint_states[_to_product(PS, att.data.target)] = pstate
+    pstore.time = ostore.time = 9 * 12                                   # current slot 9: the slot-8 attestation may be processed
+    head_before = pspec.get_head(pstore)
+    uploads = dict(pspec.stats)
     ospec.on_attestation(ostore, att)
     pspec.on_attestation(pstore, _to_product(PS, att))
     assert {v: (m.epoch, m.root) for v, m in pstore.latest_messages.items()} == {v: (m.epoch, m.root) for v, m in ostore.latest_messages.items()}
-    bad = scenarios.make_attestation(ospec, ostate2, 8, 0, corrupt="flip_bit")
+    assert pspec.get_head(pstore) == ospec.get_head(ostore)
+    for b in (0, 1, k, n_blocks - 1):
+        assert pspec.get_weight(pstore, rb[b]) == ospec.get_latest_attesting_balance(ostore, rb[b])
+    assert pspec.stats["store_uploads"] == uploads["store_uploads"] and pspec.stats["registry_uploads"] == uploads["registry_uploads"]
+    assert pspec.stats["lmd_device_updates"] == uploads["lmd_device_updates"] + 1
+    del head_before
+    bad = scenarios.make_attestation(ospec, ostate2, 8, 0, corrupt="flip_bit", head_root=rb[k], target_root=rb[k])
     with pytest.raises(AssertionError):
         pspec.on_attestation(pstore, _to_product(PS, bad))
+    # validate_on_attestation: unknown head block, a head block from the future of the attestation, an attestation from the current slot
+    unknown = scenarios.make_attestation(ospec, ostate2, 8, 0, head_root=b"\x55" * 32, target_root=rb[k])
+    later = scenarios.make_attestation(ospec, ostate2, 8, 0, head_root=rb[n_blocks - 1], target_root=rb[k])
+    for a in (unknown, later):
+        pstore.checkpoint_states[_to_product(PS, a.data.target)] = pstate
+        with pytest.raises(AssertionError):
+            pspec.on_attestation(pstore, _to_product(PS, a))
+    pstore.time = 8 * 12
+    with pytest.raises(AssertionError):
+        pspec.on_attestation(pstore, _to_product(PS, att))
+    # a block arrives (on_block is the caller's): the mirror notices the new shape and re-uploads; heads keep matching the oracle
+    new_root = b"\x77" * 32
+    for st_, S_, bs in ((ostore, OS, ostore.block_states[rb[k]]), (pstore, PS, pstore.block_states[rb[k]])):
+        st_.blocks[new_root] = S_.BeaconBlock(int(slot[k]) + 1, rb[k])
+        st_.block_states[new_root] = bs
+    pstore.time = ostore.time = 9 * 12
+    assert pspec.get_head(pstore) == ospec.get_head(ostore)
+    assert pspec.stats["store_uploads"] == uploads["store_uploads"] + 1
 
 
 def test_on_attester_slashing_marks_equivocators(env):
@@ -199,3 +228,62 @@ def test_decode_attestations_roundtrip(env):
     pspec.process_attestations(sp, got[:3])
     pspec.process_attestations(sq, atts)
     assert sp.balances == sq.balances and sp.current_epoch_participation == sq.current_epoch_participation
+
+
+def test_get_head_fast_path_at_one_million_validators():
+    """the pyspec-signature get_head(store) re-marshalled the whole Store on every call.  Now the store is
+    mirrored on the device: the first call uploads (registry: decompress + KeyValidate of 2^20 pubkeys, block tree, 2^20 latest
+    messages), later calls are the C-ABI get_head plus O(1) host checks -- under a millisecond -- and votes that arrive through
+    update_latest_messages move the device table incrementally.  Heads are checked against a from-scratch Spec (fresh upload)."""
+    import time
+    from pos_evolution_b200 import spec as PS
+    from pos_evolution_b200.engine import Engine
+    n, n_blocks = 1 << 20, 400
+    pks = scenarios.pubkeys(64)
+    rng = np.random.default_rng(12)
+    bal = rng.choice([32, 32, 32, 31, 24, 16], size=n)
+    validators = [PS.Validator(pks[i & 63], int(bal[i]) * 10**9) for i in range(n)]
+    state = PS.BeaconState(slot=64, fork=PS.Fork(), genesis_validators_root=bytes(32), validators=validators, balances=[], randao_mixes=[],
+                           block_roots=[], previous_epoch_participation=[], current_epoch_participation=[])
+    parent, slot, roots, leaf_viable = scenarios.fork_tree(n_blocks, 9)
+    rb = [bytes(r) for r in roots]
+    just = PS.Checkpoint(1, rb[0])
+    store = PS.Store(65 * 12, 0, just, just, just, rb[n_blocks - 1], set(int(v) for v in rng.choice(n, size=1000, replace=False)))
+    leaf_state = PS.BeaconState(slot=64, fork=PS.Fork(), genesis_validators_root=bytes(32), validators=[], balances=[], randao_mixes=[], block_roots=[],
+                                previous_epoch_participation=[], current_epoch_participation=[], current_justified_checkpoint=just, finalized_checkpoint=just)
+    for b in range(n_blocks):
+        store.blocks[rb[b]] = PS.BeaconBlock(int(slot[b]), rb[parent[b]] if b else bytes(32))
+        store.block_states[rb[b]] = leaf_state
+    store.checkpoint_states[just] = state
+    voted = (n_blocks - 1 - np.minimum(n_blocks - 1, rng.geometric(0.02, size=n))).astype(np.int64)
+    msgs = [PS.LatestMessage(1, rb[b]) for b in range(n_blocks)]
+    store.latest_messages = {v: msgs[voted[v]] for v in range(n) if v % 100 != 7}
+    sp = PS.Spec(PS.MAINNET, engine=Engine(0))
+    t0 = time.perf_counter()
+    h0 = sp.get_head(store)
+    first_s = time.perf_counter() - t0
+    lat = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        h = sp.get_head(store)
+        lat.append(time.perf_counter() - t0)
+        assert h == h0
+    p50 = sorted(lat)[len(lat) // 2]
+    print("Spec.get_head at 2^20 validators: first call %.2f s, then p50 %.0f us" % (first_s, p50 * 1e6))
+    assert p50 < 1e-3, "Spec.get_head after the first call must be the device call plus O(1) host work"
+    assert sp.stats["store_uploads"] == 1 and sp.stats["registry_uploads"] == 1
+    # a committee's worth of votes for a fresh fork tip, through the spec function: incremental on the device
+    att = PS.Attestation([True] * 512, PS.AttestationData(64, 0, rb[n_blocks - 2], PS.Checkpoint(0, rb[0]), PS.Checkpoint(2, rb[0])), bytes(96))
+    for k in range(8):
+        sp.update_latest_messages(store, [int(v) for v in rng.choice(n, size=512, replace=False)], att)
+    t0 = time.perf_counter()
+    h1 = sp.get_head(store)
+    assert time.perf_counter() - t0 < 1e-3 and sp.stats["store_uploads"] == 1 and sp.stats["lmd_device_updates"] == 8
+    w1 = sp.get_weight(store, rb[n_blocks - 2])
+    fresh = PS.Spec(PS.MAINNET, engine=Engine(0))
+    assert fresh.get_head(store) == h1 and fresh.get_weight(store, rb[n_blocks - 2]) == w1
+    # the weight of the justified root == every counted balance + the boost: checked against plain Python over the store
+    eq = store.equivocating_indices
+    total = sum(validators[v].effective_balance for v in store.latest_messages if v not in eq)
+    boost = (n // 32) * (int(bal.astype(object).sum()) * 10**9 // n) * 40 // 100
+    assert sp.get_weight(store, rb[0]) == total + boost

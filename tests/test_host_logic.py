@@ -163,3 +163,188 @@ def test_attestation_wire_form_matches_oracle():
         assert enc == ssz.serialize_attestation(bits, d128, sig)
         got_bits, got_data, got_sig = ssz.deserialize_attestation(enc, 2048)
         assert got_bits == bits and got_sig == sig and PS.deserialize_attestation_data(got_data) == data
+
+
+# ------------------------------------------------------------------------------------------ registry cache / store mirror (host logic)
+class _MirrorEngine:
+    """Engine stand-in that records what the host layer uploads and answers get_head / get_weights with the numpy oracle over
+    exactly the tables it was given -- so a stale or missing upload shows up as a wrong head."""
+
+    def __init__(self):
+        self.log = []
+
+    def registry_load(self, pk, eff, flags):
+        self.pk = np.array(pk, dtype=np.uint8).reshape(-1, 48).copy()
+        self.n = self.pk.shape[0]
+        self.eff, self.flags = np.array(eff, dtype=np.uint64), np.array(flags, dtype=np.uint8)
+        self.m_epoch, self.m_block = np.zeros(self.n, np.uint64), np.zeros(self.n, np.uint32)
+        self.m_has, self.equiv = np.zeros(self.n, np.uint8), np.zeros(self.n, np.uint8)
+        self.log.append("registry_load")
+        return np.ones(self.n, dtype=np.uint8)
+
+    def registry_update_balances(self, eff, flags):
+        self.eff, self.flags = np.array(eff, dtype=np.uint64), np.array(flags, dtype=np.uint8)
+        self.log.append("balances")
+
+    def tree_load(self, parent, slot, roots, viable):
+        self.parent, self.roots, self.viable = np.array(parent), np.array(roots), np.array(viable)
+        self.log.append("tree_load")
+
+    def latest_messages_load(self, epoch, blk, has, eq):
+        self.m_epoch, self.m_block = np.array(epoch, dtype=np.uint64), np.array(blk, dtype=np.uint32)
+        self.m_has, self.equiv = np.array(has, dtype=np.uint8), np.array(eq, dtype=np.uint8)
+        self.log.append("lmd_load")
+
+    def latest_messages_update(self, members, off, bits, target_epoch, block_idx, accept=None):
+        from oracle import fast
+        for a in range(len(off) - 1):
+            sel = [int(members[off[a] + j]) for j in range(off[a + 1] - off[a]) if (bits[a, j >> 3] >> (j & 7)) & 1]
+            fast.lmd_update(self.m_epoch, self.m_block, self.m_has, self.equiv, sel, int(target_epoch[a]), int(block_idx[a]))
+        self.log.append("lmd_update")
+
+    def on_attester_slashing(self, i1, i2):
+        for v in set(i1) & set(i2):
+            self.equiv[v] = 1
+        self.log.append("slashing")
+
+    def fast_aggregate_verify(self, members, off, bits, msgs, sigs):
+        self.log.append("verify")
+        return np.ones(len(off) - 1, dtype=np.uint8)
+
+    def get_weights(self, boost_idx, boost_score):
+        from oracle import fast
+        return fast.ghost_weights(self.parent, self.m_block, self.m_has, self.eff, self.flags & 1, self.equiv, boost_idx, boost_score)
+
+    def get_head(self, justified_idx, boost_idx, boost_score):
+        from oracle import fast
+        w = self.get_weights(boost_idx, boost_score)
+        return fast.ghost_head(self.parent, self.roots, fast.ghost_viable(self.parent, self.viable), w, justified_idx)
+
+
+def _mirror_world(PS, n_val=64, n_blocks=40):
+    parent, slot, roots, leaf_viable = scenarios.fork_tree(n_blocks, 6)
+    rb = [bytes(r) for r in roots]
+    rng = np.random.default_rng(3)
+    pks = [hashlib.sha256(b"pk%d" % i).digest() + bytes(16) for i in range(n_val)]
+    vals = [PS.Validator(pks[i], int(rng.integers(16, 33)) * 10**9) for i in range(n_val)]
+    state = PS.BeaconState(slot=9, fork=PS.Fork(), genesis_validators_root=bytes(32), validators=vals, balances=[0] * n_val, randao_mixes=[bytes(32)] * 64,
+                           block_roots=[bytes(32)] * 64, previous_epoch_participation=[0] * n_val, current_epoch_participation=[0] * n_val)
+    just = PS.Checkpoint(1, rb[0])
+    store = PS.Store(9 * 12, 0, just, just, just, PS.ZERO32, set())
+    for b in range(n_blocks):
+        store.blocks[rb[b]] = PS.BeaconBlock(int(slot[b]), rb[parent[b]] if b else bytes(32))
+        bs = copy_state(PS, state)
+        bs.current_justified_checkpoint, bs.finalized_checkpoint = just, just
+        store.block_states[rb[b]] = bs
+    store.checkpoint_states[just] = state
+    for v in range(n_val):
+        if rng.random() < 0.8:
+            store.latest_messages[v] = PS.LatestMessage(1, rb[int(rng.integers(n_blocks))])
+    return store, state, rb, slot
+
+
+def copy_state(PS, s):
+    import copy
+    c = copy.copy(s)
+    return c
+
+
+def _scratch_head(PS, store):
+    """the head a brand-new Spec (no caches) computes for the store"""
+    return PS.Spec(PS.MINIMAL, engine=_MirrorEngine()).get_head(store)
+
+
+def test_store_mirror_is_incremental_and_never_stale():
+    from pos_evolution_b200 import spec as PS
+    eng = _MirrorEngine()
+    sp = PS.Spec(PS.MINIMAL, engine=eng)
+    store, state, rb, slot = _mirror_world(PS)
+    h0 = sp.get_head(store)
+    assert eng.log == ["registry_load", "balances", "tree_load", "lmd_load"] and h0 == _scratch_head(PS, store)
+    eng.log.clear()
+    assert sp.get_head(store) == h0 and sp.get_weight(store, rb[0]) >= sp.get_weight(store, rb[1])
+    assert eng.log == []                                       # nothing re-uploaded, nothing re-read: the fast path
+    # votes through update_latest_messages reach the device table incrementally (K7), not by re-upload
+    att = PS.Attestation([True] * 4, PS.AttestationData(8, 0, rb[7], PS.Checkpoint(0, rb[0]), PS.Checkpoint(2, rb[0])), bytes(96))
+    sp.update_latest_messages(store, [1, 2, 3, 60], att)
+    assert eng.log == ["lmd_update"]
+    assert sp.get_head(store) == _scratch_head(PS, store)
+    assert eng.log == ["lmd_update"]
+    # an older vote changes nothing anywhere; a vote for a block the tree does not hold drops the mirror (full re-upload next time)
+    old = PS.Attestation([True] * 4, PS.AttestationData(8, 0, rb[9], PS.Checkpoint(0, rb[0]), PS.Checkpoint(1, rb[0])), bytes(96))
+    sp.update_latest_messages(store, [1, 2], old)
+    assert store.latest_messages[1].root == rb[7] and sp.get_head(store) == _scratch_head(PS, store)
+    eng.log.clear()
+    ghost = PS.Attestation([True], PS.AttestationData(8, 0, b"\x99" * 32, PS.Checkpoint(0, rb[0]), PS.Checkpoint(3, rb[0])), bytes(96))
+    sp.update_latest_messages(store, [5], ghost)
+    assert sp.get_head(store) == _scratch_head(PS, store) and "lmd_load" in eng.log
+    # the store changes shape behind the class's back: a new block, a message written straight into the dict, an equivocator
+    eng.log.clear()
+    store.blocks[b"\x42" * 32] = PS.BeaconBlock(int(slot[7]) + 1, rb[7])
+    store.block_states[b"\x42" * 32] = store.block_states[rb[7]]
+    assert sp.get_head(store) == _scratch_head(PS, store) and eng.log == ["tree_load", "lmd_load"]
+    store.latest_messages[63] = PS.LatestMessage(4, b"\x42" * 32)
+    assert sp.get_head(store) == _scratch_head(PS, store)
+    store.equivocating_indices.add(1)
+    assert sp.get_head(store) == _scratch_head(PS, store)
+    # the proposer boost moves: no upload, new score
+    eng.log.clear()
+    store.proposer_boost_root = rb[3]
+    assert sp.get_head(store) == _scratch_head(PS, store) and eng.log == []
+    # a new justified checkpoint state (other balances): balances are re-read, pubkeys are not uploaded again
+    st2 = copy_state(PS, state)
+    st2.validators = [PS.Validator(v.pubkey, 17 * 10**9) for v in state.validators]
+    store.checkpoint_states[store.justified_checkpoint] = st2
+    eng.log.clear()
+    assert sp.get_head(store) == _scratch_head(PS, store)
+    assert "registry_load" not in eng.log and "balances" in eng.log
+
+
+def test_registry_cache_is_keyed_on_content_not_on_addresses():
+    """(id(validators), len) can alias after GC and misses an in-place pubkey replacement."""
+    from pos_evolution_b200 import spec as PS
+    eng = _MirrorEngine()
+    sp = PS.Spec(PS.MINIMAL, engine=eng)
+    store, state, rb, slot = _mirror_world(PS)
+    ia = PS.IndexedAttestation([1, 2, 3], PS.AttestationData(8, 0, rb[1], PS.Checkpoint(0, rb[0]), PS.Checkpoint(1, rb[0])), bytes(96))
+    sp.are_valid_indexed_attestations(state, [ia])
+    assert eng.log.count("registry_load") == 1
+    # another state object with an equal validator set (a target checkpoint state): no second upload
+    twin = copy_state(PS, state)
+    twin.validators = [PS.Validator(v.pubkey, v.effective_balance) for v in state.validators]
+    sp.are_valid_indexed_attestations(twin, [ia])
+    assert eng.log.count("registry_load") == 1
+    # in-place replacement of one pubkey in the SAME list object: must re-upload (signatures would be checked against a stale key)
+    state.validators[10] = PS.Validator(hashlib.sha256(b"other").digest() + bytes(16), state.validators[10].effective_balance)
+    sp.are_valid_indexed_attestations(state, [ia])
+    assert eng.log.count("registry_load") == 2 and bytes(eng.pk[10]) == bytes(state.validators[10].pubkey)
+    # a same-length registry with different keys, whatever address it lands on
+    for k in range(3):
+        other = copy_state(PS, state)
+        other.validators = [PS.Validator(hashlib.sha256(b"gen%d/%d" % (k, i)).digest() + bytes(16), 32 * 10**9) for i in range(len(state.validators))]
+        sp.are_valid_indexed_attestations(other, [ia])
+        assert bytes(eng.pk[0]) == bytes(other.validators[0].pubkey)
+        del other
+    assert eng.log.count("registry_load") == 5
+
+
+def test_get_unslashed_participating_indices_matches_oracle():
+    """the product's set form called Spec.has_flag, which did not exist."""
+    from pos_evolution_b200 import spec as PS
+    ospec, ostate = scenarios.minimal_state(64, slot=17, pks=[bytes(48)] * 64)
+    rng = np.random.default_rng(1)
+    ostate.current_epoch_participation = [int(x) for x in rng.integers(0, 8, size=64)]
+    ostate.previous_epoch_participation = [int(x) for x in rng.integers(0, 8, size=64)]
+    for i in (3, 9, 40):
+        ostate.validators[i].slashed = True
+    ostate.validators[5].exit_epoch = 1
+    ps = PS.Spec(PS.MINIMAL, engine=_MirrorEngine())
+    pstate = PS.BeaconState(slot=ostate.slot, fork=PS.Fork(), genesis_validators_root=bytes(32),
+                            validators=[PS.Validator(v.pubkey, v.effective_balance, v.slashed, v.activation_epoch, v.exit_epoch) for v in ostate.validators],
+                            balances=list(ostate.balances), randao_mixes=list(ostate.randao_mixes), block_roots=list(ostate.block_roots),
+                            previous_epoch_participation=list(ostate.previous_epoch_participation),
+                            current_epoch_participation=list(ostate.current_epoch_participation))
+    for flag in range(3):
+        for epoch in (ospec.get_previous_epoch(ostate), ospec.get_current_epoch(ostate)):
+            assert ps.get_unslashed_participating_indices(pstate, flag, epoch) == ospec.get_unslashed_participating_indices(ostate, flag, epoch)
+    assert PS.Spec.has_flag(0b101, 2) and not PS.Spec.has_flag(0b101, 1) and PS.Spec.add_flag(0b001, 2) == 0b101
