@@ -470,14 +470,34 @@ def run_gpu(args):
 
     # ---- get_head latency.  N = 1: the C-ABI call incl. D2H of the head index.  N > 1: THROUGH the multi-rank path (vote scatter of
     # this rank's validators -> NCCL all-reduce of u64[10 000] -> head on every rank -> D2H), every rank in lockstep.
-    lat = []
-    hd = None
-    for i in range(250):
-        t0 = time.perf_counter()
-        hd = ep.get_head(0, boost_idx, boost) if world > 1 else eng.get_head(0, boost_idx, boost)
-        lat.append((time.perf_counter() - t0) * 1e6)
-    lat = sorted(lat[50:])
-    p50, p99 = lat[len(lat) // 2], lat[int(len(lat) * 0.99) - 1]
+    def head_latency(fn, n=250):
+        xs = []
+        h = None
+        for i in range(n):
+            t0 = time.perf_counter()
+            h = fn()
+            xs.append((time.perf_counter() - t0) * 1e6)
+        xs = sorted(xs[50:])
+        return h, xs[len(xs) // 2], xs[int(len(xs) * 0.99) - 1]
+
+    p50_nccl = p99_nccl = None
+    fused_ok = False
+    if world > 1:
+        barrier()
+        hd_nccl, p50_nccl, p99_nccl = head_latency(lambda: ep.get_head(0, boost_idx, boost, fused=False))    # scatter -> NCCL all-reduce -> tree -> D2H
+        if shard is not None:
+            barrier()
+            fused_ok = ep.enable_fused_get_head()          # collective: CUDA IPC exchange blocks on every rank, or the NCCL form everywhere
+            barrier()
+            if fused_ok:
+                hd, p50, p99 = head_latency(lambda: ep.get_head(0, boost_idx, boost, fused=True))          # one kernel per rank, reduction over NVLink peer memory
+                assert hd == hd_nccl, "fused and NCCL get_head disagree"
+            else:
+                hd, p50, p99 = hd_nccl, p50_nccl, p99_nccl
+        else:
+            hd, p50, p99 = hd_nccl, p50_nccl, p99_nccl
+    else:
+        hd, p50, p99 = head_latency(lambda: eng.get_head(0, boost_idx, boost))
     lat_local = []
     for i in range(150):
         t0 = time.perf_counter()
@@ -486,10 +506,11 @@ def run_gpu(args):
     p50_local = sorted(lat_local[50:])[50]
 
     # max over ranks
-    t = torch.tensor([ms_dev, ms_e2e, ms_agg, ms_verify, p50, p99, ms_sync, g_tma_cold, g_ldg_cold, g_tma_warm], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_dev, ms_e2e, ms_agg, ms_verify, p50, p99, ms_sync, g_tma_cold, g_ldg_cold, g_tma_warm, p50_nccl or 0.0, p99_nccl or 0.0],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e, ms_agg, ms_verify, p50, p99, ms_sync, g_tma_cold, g_ldg_cold, g_tma_warm = [float(x) for x in t.tolist()]
+    ms_dev, ms_e2e, ms_agg, ms_verify, p50, p99, ms_sync, g_tma_cold, g_ldg_cold, g_tma_warm, p50_nccl, p99_nccl = [float(x) for x in t.tolist()]
 
     if rank == 0:
         peaks = {}
@@ -531,7 +552,11 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "get_head_p50_us": p50, "get_head_p99_us": p99, "get_head_single_gpu_call_p50_us": p50_local, "head_index": head0,
-            "get_head_path": "b2_get_head (one GPU: scatter + tree + D2H)" if world == 1 else "vote scatter of N/%d validators -> NCCL all-reduce u64[10000] -> head on every rank -> D2H" % world,
+            "get_head_path": ("b2_get_head: ONE kernel (vote scatter, last CTA runs the tree phase, head written to mapped host memory)" if world == 1 else
+                              ("b2_get_head_multi: ONE kernel per rank -- scatter of N/%d validators, 64-bit reductions into every rank's accumulator over NVLink peer memory, flag exchange, tree, zero-copy result" % world
+                               if fused_ok else "vote scatter -> NCCL all-reduce u64[10000] -> tree -> D2H" + ("" if shard is None else " (peer-memory form unavailable: %s)" % ep.fused_head_error))),
+            **({"get_head_nccl_path_p50_us": p50_nccl, "get_head_nccl_path_p99_us": p99_nccl,
+                "get_head_nccl_path": "vote scatter of N/%d validators -> NCCL all-reduce u64[10000] -> tree kernel -> D2H" % world} if world > 1 else {}),
             "stage_ms": {"bls_aggregate_rank_share": ms_agg, "fast_aggregate_verify_rank_share": ms_verify,
                          **({"aggregate_and_verify_concurrent": ms_overlap} if ms_overlap is not None else {})},
             "roofline": {"bound": "hbm", "kernel": "bls.Aggregate (k_g2_decompress + k_g2_segment_sum), this rank's %d signatures" % n_loc_sig, "achieved": achieved, "peak": peak, "unit": "GB/s",

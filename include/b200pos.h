@@ -236,6 +236,19 @@ int b2_vote_weights_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, void* stream);
 int b2_vote_weights_range_dev(b2_ctx* ctx, uint64_t v_begin, uint64_t v_end, uint64_t* d_votes_preorder, void* stream);
 int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
                            uint64_t* d_weight_out /* may be NULL */, uint32_t* d_head_idx_out, void* stream);
+/* ---- get_head over ONE validator set spread over the GPUs of a box (BASELINE.json config 4; pos-evolution.md:1102-1116), one kernel
+ * per rank with the all-reduce of the vote weights fused in over NVLink peer memory (no NCCL launch between scatter and tree):
+ *   b2_fc_exchange_export  allocates this rank's exchange block (accumulators + flags, sized by the loaded tree) and returns its
+ *                          64-byte CUDA IPC handle; the host layer all-gathers the handles of the ranks (any transport);
+ *   b2_fc_exchange_open    maps every peer's block (handles64 = world x 64 bytes, in rank order);
+ *   b2_get_head_multi      COLLECTIVE (every rank, same order): scatter the votes of this rank's validators [v_begin, v_end),
+ *                          push the per-block sums into every rank's accumulator with 64-bit reductions over NVLink, flag
+ *                          exchange, tree phase on the complete accumulator; returns the same head on every rank.
+ * One process per GPU, at most 8 ranks, all on one NVLink/NVSwitch domain.  Re-export after b2_tree_load. */
+int b2_fc_exchange_export(b2_ctx* ctx, uint8_t* handle64_out);
+int b2_fc_exchange_open(b2_ctx* ctx, int rank, int world, const uint8_t* handles64);
+int b2_get_head_multi(b2_ctx* ctx, uint64_t v_begin, uint64_t v_end, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
+                      uint32_t* head_idx_out);
 uint32_t b2_tree_size(b2_ctx* ctx);
 /* profiling aid: SM-clock stamps of the phases of the context's last get_head (vote scatter of CTA 0, tree phases); u64[32] */
 int b2_debug_head_clocks(b2_ctx* ctx, uint64_t* out32);

@@ -73,6 +73,9 @@ SIGNATURES = {
     "b2_gather_probe_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_int, c_void_p, c_void_p]),
     "b2_head_from_votes_dev": (c_int, [c_void_p, c_void_p, c_uint32, c_int32, c_uint64, c_void_p, c_void_p, c_void_p]),
     "b2_tree_size": (c_uint32, [c_void_p]),
+    "b2_fc_exchange_export": (c_int, [c_void_p, c_void_p]),
+    "b2_fc_exchange_open": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "b2_get_head_multi": (c_int, [c_void_p, c_uint64, c_uint64, c_uint32, c_int32, c_uint64, c_void_p]),
     "b2_debug_head_clocks": (c_int, [c_void_p, c_void_p]),
 }
 

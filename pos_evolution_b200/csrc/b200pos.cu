@@ -17,6 +17,15 @@
 
 using namespace b2;
 
+// dynamic shared memory of the tree phase in its shared-memory form: votes/prefix/weights u64[n+1], packed word u32[n], marks u32[n+1],
+// and -- when it still fits -- the work list u32[n] of the marking phase
+static size_t tree_smem_bytes(ghost_tree_args& A) {
+    const size_t base = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8 + 8;
+    const size_t with_list = base + (size_t)A.n * 4;
+    A.hard_list = with_list <= 226 * 1024 ? 1 : 0;
+    return A.hard_list ? with_list : base;
+}
+
 struct dbuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -87,6 +96,14 @@ struct b2_ctx {
     volatile uint32_t* h_head = nullptr;
     uint32_t* d_head_host = nullptr;
     uint32_t head_seq = 0;
+    // multi-GPU get_head over NVLink peer memory (b2_fc_exchange_*): this rank's exchange block = accumulators 2 x n_blocks u64 followed by
+    // flag rows 2 x B2_MAX_PEERS u32; peers' blocks opened through CUDA IPC
+    void* fc_block = nullptr;
+    size_t fc_block_bytes = 0;
+    uint32_t fc_blocks_cap = 0;                       // n_blocks the block was sized for
+    void* fc_peer[B2_MAX_PEERS] = {nullptr};
+    int fc_rank = -1, fc_world = 0;
+    uint32_t fc_seq = 0;
     unsigned long long* d_dbg = nullptr;              // clock64() stamps of the last get_head's phases (b2_debug_head_clocks)
     uint32_t* d_guard = nullptr;                      // device-side input guard word (kernels.cuh GuardBits), read by b2_guard_flags
     unsigned long long fc_min_key = 0;
@@ -97,6 +114,8 @@ struct b2_ctx {
     // block tree
     uint32_t n_blocks = 0;
     uint32_t *d_pre = nullptr, *d_inv = nullptr, *d_size_keep = nullptr, *d_rank = nullptr, *d_next = nullptr, *d_gsize = nullptr;
+    bool packed_ok = false;
+    uint32_t* d_packed = nullptr;     // size | rank << 15 | keep << 31 in pre-order (trees of < 32 768 blocks), else nullptr
     unsigned long long *d_votes = nullptr, *d_prefix = nullptr, *d_weight = nullptr, *d_w2 = nullptr;
     uint32_t* d_head = nullptr;
     // scratch
@@ -224,6 +243,7 @@ int b2_init(int device, b2_ctx** out) {
         e = cudaHostGetDevicePointer((void**)&ctx->d_head_host, (void*)ctx->h_head, 0);
     }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_get_head_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_get_head_fused_nvl, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (const char* ev = getenv("B2_HEAD_FUSED")) ctx->head_fused = atoi(ev) != 0;
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_rlc_seed, 32);
     if (e == cudaSuccess) e = cudaMemset(ctx->d_rlc_seed, 0, 32);
@@ -270,7 +290,7 @@ void b2_destroy(b2_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {ctx->d_part[0], ctx->d_part[1], ctx->d_part_first, ctx->d_records, ctx->d_valid, ctx->d_eff, ctx->d_flags, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_pre,
+    void* ptrs[] = {ctx->d_packed, ctx->d_part[0], ctx->d_part[1], ctx->d_part_first, ctx->d_records, ctx->d_valid, ctx->d_eff, ctx->d_flags, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_pre,
                     ctx->d_inv, ctx->d_size_keep, ctx->d_gsize, ctx->d_w2, ctx->d_rank, ctx->d_next, ctx->d_votes, ctx->d_prefix,
                     ctx->d_weight, ctx->d_head};
     for (void* p : ptrs)
@@ -299,6 +319,9 @@ void b2_destroy(b2_ctx* ctx) {
     if (ctx->d_rlc_seed) cudaFree(ctx->d_rlc_seed);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+    for (int r = 0; r < B2_MAX_PEERS; r++)
+        if (ctx->fc_peer[r] && r != ctx->fc_rank) cudaIpcCloseMemHandle(ctx->fc_peer[r]);
+    if (ctx->fc_block) cudaFree(ctx->fc_block);
     if (ctx->h_head) cudaFreeHost((void*)ctx->h_head);
     if (ctx->ev_votes_done) cudaEventDestroy(ctx->ev_votes_done);
     delete ctx;
@@ -1254,19 +1277,22 @@ int b2_tree_load(b2_ctx* ctx, const uint32_t* parent, const uint64_t* slot, cons
     CK(cudaSetDevice(ctx->device));
     int rc;
     // everything the tree kernel reads is stored in pre-order
-    std::vector<uint32_t> inv(n), size_keep(n), rank_p(n);
+    std::vector<uint32_t> inv(n), size_keep(n), rank_p(n), packed(n);
     for (uint32_t b = 0; b < n; b++) {
         const uint32_t p = pre[b];
         inv[p] = b;
         size_keep[p] = size[b] | (keep[b] ? 0x80000000u : 0u);
         rank_p[p] = rank[b];
+        packed[p] = (size[b] & 0x7fffu) | ((rank[b] & 0x7fffu) << 15) | (keep[b] ? 0x80000000u : 0u);
     }
     if ((rc = dev_alloc(ctx, &ctx->d_pre, n)) || (rc = dev_alloc(ctx, &ctx->d_inv, n)) || (rc = dev_alloc(ctx, &ctx->d_size_keep, n)) ||
         (rc = dev_alloc(ctx, &ctx->d_rank, n)) || (rc = dev_alloc(ctx, &ctx->d_next, (size_t)n + 1)) || (rc = dev_alloc(ctx, &ctx->d_gsize, n)) ||
         (rc = dev_alloc(ctx, &ctx->d_votes, n)) || (rc = dev_alloc(ctx, &ctx->d_prefix, (size_t)n + 1)) || (rc = dev_alloc(ctx, &ctx->d_w2, n)) ||
-        (rc = dev_alloc(ctx, &ctx->d_weight, n)) || (rc = dev_alloc(ctx, &ctx->d_head, 1)))
+        (rc = dev_alloc(ctx, &ctx->d_weight, n)) || (rc = dev_alloc(ctx, &ctx->d_head, 1)) || (rc = dev_alloc(ctx, &ctx->d_packed, n)))
         return rc;
     cudaStream_t s = ctx->s_main;
+    CK(cudaMemcpyAsync(ctx->d_packed, packed.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    ctx->packed_ok = n < 32768;
     CK(cudaMemcpyAsync(ctx->d_pre, pre.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_inv, inv.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_size_keep, size_keep.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
@@ -1323,6 +1349,7 @@ int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t jus
     A.inv = ctx->d_inv;
     A.size_keep = ctx->d_size_keep;
     A.rank = ctx->d_rank;
+    A.packed = ctx->packed_ok ? ctx->d_packed : nullptr;
     A.votes = (unsigned long long*)d_votes_preorder;
     A.g_w = ctx->d_prefix;
     A.g_w2 = ctx->d_w2;
@@ -1336,6 +1363,8 @@ int b2_head_from_votes_dev(b2_ctx* ctx, uint64_t* d_votes_preorder, uint32_t jus
     size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8 + 8;
     A.use_smem = smem <= 226 * 1024 && A.n <= 15 * 1024;   // 227 KB per block minus the kernel's static shared memory
     A.dbg = ctx->d_dbg;
+    A.hard_list = 0;
+    if (A.use_smem && A.packed) smem = tree_smem_bytes(A);
     k_ghost_tree<<<1, 1024, A.use_smem ? smem : 0, s>>>(A);
     CKL(ctx);
     return B2_OK;
@@ -1355,12 +1384,103 @@ int b2_get_weights(b2_ctx* ctx, int32_t boost_idx, uint64_t boost_score, uint64_
 }
 
 static void fill_tree_args(b2_ctx* ctx, ghost_tree_args& A, uint64_t* d_votes_preorder, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
+                           uint64_t* d_weight_out, uint32_t* d_head_idx_out);
+
+// ---- multi-GPU get_head with the all-reduce fused in over NVLink peer memory (k_get_head_fused_nvl)
+static size_t fc_acc_bytes(uint32_t n_blocks) { return ((size_t)2 * n_blocks * 8 + 255) & ~(size_t)255; }
+int b2_fc_exchange_export(b2_ctx* ctx, uint8_t* handle64_out) {
+    B2_NVTX;
+    REQUIRE(ctx && handle64_out, "fc_exchange_export: bad arguments");
+    REQUIRE(ctx->n_blocks > 0, "fc_exchange_export: load the block tree first (the exchange block is sized by it)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    for (int r = 0; r < B2_MAX_PEERS; r++) {
+        if (ctx->fc_peer[r] && r != ctx->fc_rank) CK(cudaIpcCloseMemHandle(ctx->fc_peer[r]));
+        ctx->fc_peer[r] = nullptr;
+    }
+    if (ctx->fc_block) CK(cudaFree(ctx->fc_block));
+    ctx->fc_block = nullptr;
+    ctx->fc_rank = -1;
+    ctx->fc_world = 0;
+    ctx->fc_block_bytes = fc_acc_bytes(ctx->n_blocks) + 2 * B2_MAX_PEERS * sizeof(unsigned int);
+    CK(cudaMalloc(&ctx->fc_block, ctx->fc_block_bytes));
+    CK(cudaMemset(ctx->fc_block, 0, ctx->fc_block_bytes));
+    ctx->fc_blocks_cap = ctx->n_blocks;
+    ctx->fc_seq = 0;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->fc_block));
+    memcpy(handle64_out, &h, 64);
+    return B2_OK;
+}
+int b2_fc_exchange_open(b2_ctx* ctx, int rank, int world, const uint8_t* handles64) {
+    B2_NVTX;
+    REQUIRE(ctx && handles64 && world >= 1 && world <= B2_MAX_PEERS && rank >= 0 && rank < world, "fc_exchange_open: bad arguments");
+    REQUIRE(ctx->fc_block, "fc_exchange_open: call b2_fc_exchange_export first");
+    CK(cudaSetDevice(ctx->device));
+    for (int r = 0; r < world; r++) {
+        if (r == rank) {
+            ctx->fc_peer[r] = ctx->fc_block;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles64 + 64 * (size_t)r, 64);
+        CK(cudaIpcOpenMemHandle(&ctx->fc_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ctx->fc_rank = rank;
+    ctx->fc_world = world;
+    return B2_OK;
+}
+int b2_get_head_multi(b2_ctx* ctx, uint64_t v_begin, uint64_t v_end, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score, uint32_t* head_idx_out) {
+    B2_NVTX;
+    REQUIRE(ctx && head_idx_out, "get_head_multi: bad arguments");
+    REQUIRE(ctx->n_val > 0 && ctx->n_blocks > 0, "get_head_multi: registry or tree not loaded");
+    REQUIRE(ctx->fc_world >= 1 && ctx->fc_blocks_cap == ctx->n_blocks, "get_head_multi: exchange block not opened for this tree (b2_fc_exchange_export / _open)");
+    REQUIRE(v_begin <= v_end && v_end <= ctx->n_val, "get_head_multi: validator range outside the registry");
+    REQUIRE(justified_idx < ctx->n_blocks && boost_idx < (int32_t)ctx->n_blocks, "get_head_multi: block index out of range");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->s_main;
+    ghost_tree_args A;
+    fill_tree_args(ctx, A, (uint64_t*)ctx->d_votes, justified_idx, boost_idx, boost_score, nullptr, ctx->d_head);
+    REQUIRE(A.use_smem && A.packed, "get_head_multi: the tree does not fit the shared-memory form (< ~14 500 blocks)");
+    const uint64_t n = v_end - v_begin;
+    ghost_votes_args V = {n, ctx->d_lmd_key + v_begin, ctx->d_lmd_block + v_begin, ctx->d_equiv + v_begin, ctx->d_flags + v_begin, ctx->d_eff + v_begin,
+                          ctx->fc_min_key, 1u, ctx->fc_exclude_slashed ? 3u : 1u};
+    ghost_peer_args P;
+    const uint32_t seq = ++ctx->fc_seq ? ctx->fc_seq : ++ctx->fc_seq;                  // the collective call number (same on every rank)
+    const uint32_t hseq = ++ctx->head_seq ? ctx->head_seq : ++ctx->head_seq;            // this context's host-slot sequence number
+    for (int r = 0; r < B2_MAX_PEERS; r++) {
+        P.acc[r] = r < ctx->fc_world ? (unsigned long long*)ctx->fc_peer[r] : nullptr;
+        P.flags[r] = r < ctx->fc_world ? (unsigned int*)((char*)ctx->fc_peer[r] + fc_acc_bytes(ctx->n_blocks)) : nullptr;
+    }
+    P.rank = (uint32_t)ctx->fc_rank;
+    P.world = (uint32_t)ctx->fc_world;
+    P.seq = seq;
+    const size_t smem = tree_smem_bytes(A);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->n_sm, (n + 1023) / 1024));
+    k_get_head_fused_nvl<<<grid, 1024, smem, s>>>(V, A, P, ctx->d_ticket, (unsigned long long*)ctx->d_votes, ctx->d_head_host, hseq);
+    CKL(ctx);
+    CK(cudaEventRecord(ctx->ev_votes_done, s));
+    volatile unsigned long long* slot64 = reinterpret_cast<volatile unsigned long long*>(ctx->h_head);
+    unsigned long long got = 0;
+    for (uint64_t spins = 0; (uint32_t)((got = *slot64) >> 32) != hseq; spins++) {
+        if ((spins & 0xfffff) == 0xfffff) {
+            cudaError_t q = cudaStreamQuery(s);
+            if (q != cudaErrorNotReady && q != cudaSuccess) return fail_cuda(ctx, q, "get_head_multi kernel");
+        }
+    }
+    *head_idx_out = (uint32_t)got;
+    return B2_OK;
+}
+
+static void fill_tree_args(b2_ctx* ctx, ghost_tree_args& A, uint64_t* d_votes_preorder, uint32_t justified_idx, int32_t boost_idx, uint64_t boost_score,
                            uint64_t* d_weight_out, uint32_t* d_head_idx_out) {
     A.n = ctx->n_blocks;
     A.pre = ctx->d_pre;
     A.inv = ctx->d_inv;
     A.size_keep = ctx->d_size_keep;
     A.rank = ctx->d_rank;
+    A.packed = ctx->packed_ok ? ctx->d_packed : nullptr;
     A.votes = (unsigned long long*)d_votes_preorder;
     A.g_w = ctx->d_prefix;
     A.g_w2 = ctx->d_w2;
@@ -1374,6 +1494,7 @@ static void fill_tree_args(b2_ctx* ctx, ghost_tree_args& A, uint64_t* d_votes_pr
     const size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8 + 8;
     A.use_smem = smem <= 226 * 1024 && A.n <= 15 * 1024;   // 227 KB per block minus the kernel's static shared memory
     A.dbg = ctx->d_dbg;
+    A.hard_list = 0;
 }
 
 // Diagnostics: SM-clock stamps (clock64) of the phases of the LAST b2_get_head / b2_head_from_votes_dev of this context: out32[0..7] =
@@ -1396,22 +1517,24 @@ int b2_get_head(b2_ctx* ctx, uint32_t justified_idx, int32_t boost_idx, uint64_t
     cudaStream_t s = ctx->s_main;
     ghost_tree_args A;
     fill_tree_args(ctx, A, (uint64_t*)ctx->d_votes, justified_idx, boost_idx, boost_score, nullptr, ctx->d_head);
-    if (ctx->head_fused && A.use_smem) {
+    if (ctx->head_fused && A.use_smem && A.packed) {
         // one launch; the kernel writes (head, sequence) into mapped pinned memory and the host spins on the sequence number
         CK(cudaSetDevice(ctx->device));
         ghost_votes_args V = {ctx->n_val, ctx->d_lmd_key, ctx->d_lmd_block, ctx->d_equiv, ctx->d_flags, ctx->d_eff, ctx->fc_min_key, 1u,
                               ctx->fc_exclude_slashed ? 3u : 1u};
         const uint32_t seq = ++ctx->head_seq ? ctx->head_seq : ++ctx->head_seq;       // never 0
-        const size_t smem = ((size_t)A.n + 1) * 8 + (size_t)A.n * 8 + 8;
+        const size_t smem = tree_smem_bytes(A);
         const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->n_sm, (ctx->n_val + 1023) / 1024);
         k_get_head_fused<<<grid, 1024, smem, s>>>(V, A, ctx->d_ticket, ctx->d_head_host, seq);
         CKL(ctx);
         CK(cudaEventRecord(ctx->ev_votes_done, s));
-        for (uint64_t spins = 0; ctx->h_head[1] != seq; spins++) {
+        volatile unsigned long long* slot64 = reinterpret_cast<volatile unsigned long long*>(ctx->h_head);
+        unsigned long long got = 0;
+        for (uint64_t spins = 0; (uint32_t)((got = *slot64) >> 32) != seq; spins++) {
             if ((spins & 0xfffff) == 0xfffff) {                 // every ~1M polls: has the kernel died?
                 cudaError_t q = cudaStreamQuery(s);
                 if (q != cudaErrorNotReady && q != cudaSuccess) return fail_cuda(ctx, q, "get_head kernel");
-                if (q == cudaSuccess && ctx->h_head[1] != seq) {    // finished without publishing: should not happen; fall back to a copy
+                if (q == cudaSuccess && (uint32_t)(*slot64 >> 32) != seq) {    // finished without publishing: should not happen; fall back to a copy
                     uint32_t h = 0;
                     CK(cudaMemcpy(&h, ctx->d_head, 4, cudaMemcpyDeviceToHost));
                     *head_idx_out = h;
@@ -1419,7 +1542,7 @@ int b2_get_head(b2_ctx* ctx, uint32_t justified_idx, int32_t boost_idx, uint64_t
                 }
             }
         }
-        *head_idx_out = ctx->h_head[0];
+        *head_idx_out = (uint32_t)got;
         return B2_OK;
     }
     if ((rc = b2_vote_weights_dev(ctx, (uint64_t*)ctx->d_votes, s))) return rc;

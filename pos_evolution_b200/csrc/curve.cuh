@@ -252,26 +252,27 @@ HD void g1_compress(const g1_jac& p, uint8_t* out) {
 HDN int g2_decompress(const uint8_t* in, g2_aff& out, uint32_t* tab = nullptr, uint32_t tab_stride = 0) {
     fp x1c, x0c;
     uint8_t b0;
-#if defined(__CUDA_ARCH__) && !defined(B2_SIG_BYTE_LOADS)
-    if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
-        // 96 contiguous bytes per signature: six 128-bit loads instead of 96 byte loads
-        uint32_t w[24];
+#if defined(__CUDA_ARCH__) && defined(B2_SIG_VECTOR_LOADS)
+    {
+        // 96 contiguous bytes per signature as six 128-bit loads (needs 16-byte aligned signature arrays).  MEASURED SLOWER than the
+        // byte loads below and therefore off: 29.47 vs 29.23 ms for 2^20 decompressions, twice, tools/decompress_bench.cu
+        // (profiles/r2_decompress_bench_sigloads.jsonl).  The loads are 0.04 % of the kernel's instructions either way; the 24 live
+        // words at the top of the function cost the register allocation of what follows more than the 90 saved LDG.U8 return.
         const uint4* in4 = reinterpret_cast<const uint4*>(in);
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const uint4 v = in4[k];
-            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-        }
-        b0 = (uint8_t)(w[0] & 0xffu);
-        x1c = fp_from_be48_words(w);
-        x0c = fp_from_be48_words(w + 12);
-    } else
-#endif
+        const uint4 q0 = in4[0], q1 = in4[1], q2 = in4[2], q3 = in4[3], q4 = in4[4], q5 = in4[5];
+        const uint32_t w1[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+        const uint32_t w0[12] = {q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w};
+        b0 = (uint8_t)(q0.x & 0xffu);
+        x1c = fp_from_be48_words(w1);
+        x0c = fp_from_be48_words(w0);
+    }
+#else
     {
         b0 = in[0];
         x1c = fp_from_be48(in);
         x0c = fp_from_be48(in + 48);
     }
+#endif
     if (!(b0 & 0x80)) return DEC_BAD;
     x1c.l[11] &= 0x1fffffffu;
     if (b0 & 0x40) {

@@ -609,6 +609,7 @@ struct ghost_tree_args {
     const uint32_t* inv;         // pre-order position -> block
     const uint32_t* size_keep;   // pre-order: subtree size | (get_filtered_block_tree membership << 31)
     const uint32_t* rank;        // pre-order: lexicographic rank of the 32-byte root (tie-break of :1114-1116)
+    const uint32_t* packed;      // pre-order, trees of < 32 768 blocks: size | rank << 15 | keep << 31 (one word: the shared-memory form)
     unsigned long long* votes;   // in: direct votes in pre-order; zeroed on exit
     unsigned long long* g_w;     // global fallback scratch n+1 (prefix sums)
     unsigned long long* g_w2;    // global fallback scratch n (weights)
@@ -620,6 +621,7 @@ struct ghost_tree_args {
     int32_t boost_idx;
     unsigned long long boost_score;
     int use_smem;
+    int hard_list;               // shared-memory form: the launch reserved u32[n] more for the work list of the marking phase
     unsigned long long* dbg;     // optional: thread 0 of the tree phase stores clock64() at its phase boundaries (b2_debug_head_clocks)
 };
 
@@ -758,17 +760,230 @@ __device__ __forceinline__ void ghost_tree_body(const ghost_tree_args& A, unsign
     if (tid == 0) {
         const uint32_t h = (A.justified < n) ? A.inv[max(head_pos, jp)] : 0xffffffffu;
         *A.head_out = h;
-        if (host_out) {                         // zero-copy result: mapped pinned host memory, head first, then the sequence number
-            reinterpret_cast<volatile uint32_t*>(host_out)[0] = h;
-            __threadfence_system();
-            reinterpret_cast<volatile uint32_t*>(host_out)[1] = host_seq;
-        }
+        if (host_out) *reinterpret_cast<volatile unsigned long long*>(host_out) = (unsigned long long)h | ((unsigned long long)host_seq << 32);
     }
     B2_TREE_STAMP(15);
 }
+// ---- the shared-memory form of the tree phase (every tree that fits: < ~14 500 blocks), specialised after the phase clocks of the
+// generic body (profiles/r2_head_clocks_v1.jsonl: 44 900 SM clocks = 23.6 us, of which marking 17 800, staging 8 700, first scan
+// 6 100): (1) all arrays are __shared__ pointers -- LDS/STS instead of generic LD/ST whose address space is resolved at run time;
+// (2) the per-block word packs subtree size, root rank and the filter bit, so a tie between equal-weight siblings costs no global
+// load (the generic body reads A.rank[] from global memory inside the child loop); (3) the staging loop issues all of a thread's
+// global loads before using any; (4) the prefix sums are row-wise warp scans (lane-contiguous: no bank conflicts) with one
+// cross-warp step; (5) the head and its sequence number leave in ONE 64-bit store to mapped host memory.
+#define B2_SZ(x) ((x) & 0x7fffu)
+#define B2_RK(x) (((x) >> 15) & 0x7fffu)
+#define B2_KEEP(x) ((x) >> 31)
+// exclusive prefix sum of x[0..n) in shared memory, x[n] = total.  Warp w owns the contiguous rows [w*rows, (w+1)*rows) of 32 elements.
+template <class T> __device__ __forceinline__ void smem_exclusive_scan(T* x, uint32_t n, T* warp_tot) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const uint32_t rows = ((n + 31) / 32 + nwarp - 1) / nwarp;            // rows of 32 per warp
+    const uint32_t base = warp * rows * 32;
+    T carry = 0;
+    // eight rows at a time: their shuffle scans are independent chains the scheduler interleaves (a u64 shuffle step is two dependent
+    // SHFLs of ~25 cycles; row after row that chain was 6 600 clocks for 10 000 elements, profiles/r2_head_clocks_v2.jsonl)
+    constexpr int G = 8;
+    for (uint32_t r0 = 0; r0 < rows; r0 += G) {
+        T v[G], incl[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const uint32_t i = base + (r0 + g) * 32 + lane;
+            v[g] = (r0 + g < rows && i < n) ? x[i] : (T)0;
+            incl[g] = v[g];
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const T o = __shfl_up_sync(B2_FULL_MASK, incl[g], d);
+                if ((int)lane >= d) incl[g] += o;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const uint32_t i = base + (r0 + g) * 32 + lane;
+            const T tot = __shfl_sync(B2_FULL_MASK, incl[g], 31);
+            if (r0 + g < rows && i < n) x[i] = carry + incl[g] - v[g];   // exclusive within the warp's range
+            carry += tot;
+        }
+    }
+    if (lane == 0) warp_tot[warp] = carry;
+    __syncthreads();
+    if (warp == 0) {
+        const T w = lane < nwarp ? warp_tot[lane] : (T)0;
+        T wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const T o = __shfl_up_sync(B2_FULL_MASK, wi, d);
+            if ((int)lane >= d) wi += o;
+        }
+        warp_tot[lane] = wi - w;                                            // exclusive offset of each warp
+        if (lane == 31) x[n] = wi;                                          // grand total
+    }
+    __syncthreads();
+    const T off = warp_tot[warp];
+    if (off != 0)
+        for (uint32_t r = 0; r < rows; r++) {
+            const uint32_t i = base + r * 32 + lane;
+            if (i < n) x[i] += off;
+        }
+    __syncthreads();
+}
+__device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsigned long long* smem_u64, uint32_t* host_out, uint32_t host_seq) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ uint32_t warp_tot32[32];
+    __shared__ uint32_t head_pos, n_hard;
+    constexpr int MAXPT = 15;                                               // n <= 15 * 1024 (b2_head_from_votes_dev's use_smem test)
+    const uint32_t n = A.n, tid = threadIdx.x, T = blockDim.x;
+    B2_TREE_STAMP(0);
+    unsigned long long* W = smem_u64;                                       // n+1: votes -> prefix sums -> weights
+    uint32_t* sz = reinterpret_cast<uint32_t*>(smem_u64 + (n + 1));         // n: size | rank << 15 | keep << 31
+    uint32_t* mark = sz + n;                                                // n+1: marks -> counts
+    const uint32_t boost_p = A.boost_idx >= 0 ? __ldg(A.pre + A.boost_idx) : 0xffffffffu;
+    const uint32_t jp = A.justified < n ? __ldg(A.pre + A.justified) : 0;
+    if (tid == 0) head_pos = 0;
+    {
+        unsigned long long v[MAXPT];
+        uint32_t s[MAXPT];
+#pragma unroll
+        for (int j = 0; j < MAXPT; j++) {                                   // every global load of the thread in flight at once
+            const uint32_t p = tid + j * T;
+            v[j] = p < n ? __ldcg(A.votes + p) : 0ull;
+            s[j] = p < n ? __ldg(A.packed + p) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < MAXPT; j++) {
+            const uint32_t p = tid + j * T;
+            if (p < n) {
+                A.votes[p] = 0;                                             // leave the global accumulator clean for the next call
+                W[p] = v[j] + (p == boost_p ? A.boost_score : 0ull);
+                sz[p] = s[j];
+                mark[p] = 0;
+            }
+        }
+    }
+    if (tid == 0) mark[n] = 0;
+    __syncthreads();
+    B2_TREE_STAMP(1);
+    smem_exclusive_scan(W, n, warp_tot);
+    B2_TREE_STAMP(2);
+    {
+        unsigned long long wreg[MAXPT];
+#pragma unroll
+        for (int j = 0; j < MAXPT; j++) {
+            const uint32_t p = tid + j * T;
+            if (p < n) wreg[j] = W[p + B2_SZ(sz[p])] - W[p];                 // weight = difference of two prefix sums
+        }
+        __syncthreads();
+        B2_TREE_STAMP(3);
+#pragma unroll
+        for (int j = 0; j < MAXPT; j++) {
+            const uint32_t p = tid + j * T;
+            if (p < n) W[p] = wreg[j];
+        }
+    }
+    __syncthreads();
+    B2_TREE_STAMP(4);
+    if (A.weight_out)
+        for (uint32_t b = tid; b < n; b += T) A.weight_out[b] = W[A.pre[b]];
+    // every child that is not its parent's best child gets +1 at its position and -1 just past its subtree.
+    // Most parents of a block tree have ONE child (the chain); it is trivially the best child and nothing is marked.  Looping over
+    // parents thread by thread makes every warp wait for its lane with the most children in each of its ~10 trips (13 800 clocks).
+    // When the launch left room for a work list (A.hard_list), the parents that need the loops are first compacted into it and
+    // then spread evenly over the block.
+    auto mark_children = [&](uint32_t p, uint32_t sk) {
+        const uint32_t end = p + B2_SZ(sk);
+        uint32_t best = 0xffffffffu, best_rk = 0;
+        if (B2_KEEP(sk)) {
+            unsigned long long bw = 0;
+            for (uint32_t c = p + 1; c < end;) {
+                const uint32_t sc = sz[c];
+                if (B2_KEEP(sc)) {
+                    const unsigned long long w = W[c];
+                    if (best == 0xffffffffu || w > bw || (w == bw && B2_RK(sc) > best_rk)) {
+                        best = c;
+                        bw = w;
+                        best_rk = B2_RK(sc);
+                    }
+                }
+                c += B2_SZ(sc);
+            }
+        }
+        for (uint32_t c = p + 1; c < end;) {
+            const uint32_t step = B2_SZ(sz[c]);
+            if (c != best) {
+                atomicAdd(&mark[c], 1u);
+                atomicAdd(&mark[c + step], 0xffffffffu);                    // -1 (mod 2^32); position n is the sentinel slot
+            }
+            c += step;
+        }
+    };
+    if (A.hard_list) {
+        uint32_t* list = mark + (n + 1);                                    // u32[n], behind the three arrays
+        if (tid == 0) n_hard = 0;
+        __syncthreads();
+        const uint32_t lane = tid & 31;
+#pragma unroll 1
+        for (uint32_t p0 = 0; p0 < n; p0 += T) {
+            const uint32_t p = p0 + tid;
+            bool hard = false;
+            if (p < n) {
+                const uint32_t sk = sz[p];
+                if (B2_SZ(sk) > 1) {
+                    const uint32_t s1 = sz[p + 1];                          // p has a child, so p + 1 < n
+                    hard = !(B2_SZ(s1) + 1 == B2_SZ(sk) && B2_KEEP(sk) && B2_KEEP(s1));      // not "one child, kept": needs the loops
+                }
+            }
+            const unsigned m = __ballot_sync(B2_FULL_MASK, hard);
+            uint32_t at = 0;
+            if (lane == 0 && m) at = atomicAdd(&n_hard, (uint32_t)__popc(m));
+            at = __shfl_sync(B2_FULL_MASK, at, 0);
+            if (hard) list[at + __popc(m & ((1u << lane) - 1u))] = p;
+        }
+        __syncthreads();
+        const uint32_t nh = n_hard;
+        for (uint32_t i = tid; i < nh; i += T) {
+            const uint32_t p = list[i];
+            mark_children(p, sz[p]);
+        }
+    } else {
+        for (uint32_t p = tid; p < n; p += T) {
+            const uint32_t sk = sz[p];
+            if (B2_SZ(sk) > 1) mark_children(p, sk);
+        }
+    }
+    __syncthreads();
+    B2_TREE_STAMP(5);
+    smem_exclusive_scan(mark, n, warp_tot32);
+    B2_TREE_STAMP(6);
+    const uint32_t base = mark[jp + 1];
+    const uint32_t jend = jp + B2_SZ(sz[jp]);
+    uint32_t best_pos = 0;
+    bool have = false;
+    for (uint32_t p = jp + tid; p < jend; p += T) {
+        if (mark[p + 1] == base) {
+            best_pos = p;
+            have = true;
+        }
+    }
+    if (have) atomicMax(&head_pos, best_pos);
+    __syncthreads();
+    B2_TREE_STAMP(7);
+    if (tid == 0) {
+        const uint32_t h = (A.justified < n) ? A.inv[max(head_pos, jp)] : 0xffffffffu;
+        *A.head_out = h;
+        if (host_out)                           // zero-copy result: (head, sequence number) in one 64-bit store to mapped pinned memory
+            *reinterpret_cast<volatile unsigned long long*>(host_out) = (unsigned long long)h | ((unsigned long long)host_seq << 32);
+    }
+    B2_TREE_STAMP(15);
+}
+
 __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
     extern __shared__ unsigned long long smem_u64[];
-    ghost_tree_body(A, smem_u64, nullptr, 0);
+    if (A.use_smem && A.packed)
+        ghost_tree_smem(A, smem_u64, nullptr, 0);
+    else
+        ghost_tree_body(A, smem_u64, nullptr, 0);
 }
 // get_head in ONE launch (b2_get_head): every CTA scatters its share of the votes (K8), the CTA that finishes last -- elected by a
 // ticket counter -- runs the tree phase (K9) on the completed vote array and writes the head straight into mapped pinned host memory
@@ -795,7 +1010,62 @@ __global__ void __launch_bounds__(1024) k_get_head_fused(ghost_votes_args V, gho
     if (!is_last) return;
     __threadfence();                                   // the other CTAs' vote atomics are visible (they live in L2)
     if (threadIdx.x == 0) *ticket = 0;                 // re-armed for the next call
-    ghost_tree_body(A, smem_u64, host_out, host_seq);
+    ghost_tree_smem(A, smem_u64, host_out, host_seq);  // (the fused kernel is only launched for trees in the shared-memory form)
+}
+
+// get_head over ONE validator set spread over the GPUs of a box (BASELINE.json config 4: N/8 validators per GPU) as one kernel per rank,
+// the all-reduce of the per-block vote weights fused into it over NVLink peer memory:
+//   1. every CTA scatters its share of THIS RANK's validators into the rank's local vote vector (as k_get_head_fused);
+//   2. the CTA that finishes last PUSHES the rank's vector into the accumulator of every rank of the box -- 64-bit reductions
+//      (red.add) straight into peer memory mapped through CUDA IPC, 80 KB per peer through NVSwitch -- then raises its flag on every
+//      peer (system-scope release) and waits until every rank's flag for this call has arrived in its own flag row;
+//   3. it then runs the tree phase on the now complete accumulator and publishes the head (zero-copy).
+// No NCCL launch, no second kernel, no host round trip between the stages.  Calls are collective: every rank must issue them in the
+// same order (the sequence number).  Accumulators and flag rows are double-buffered by the parity of the sequence number, so a rank
+// that races ahead into call k+1 never touches the buffers call k is still reading.
+#define B2_MAX_PEERS 8
+struct ghost_peer_args {
+    unsigned long long* acc[B2_MAX_PEERS];     // acc[r]: rank r's accumulators, 2 x n_blocks u64 (parity-major), peer-mapped
+    unsigned int* flags[B2_MAX_PEERS];         // flags[r]: rank r's flag rows, 2 x B2_MAX_PEERS u32
+    uint32_t rank, world, seq;
+};
+__global__ void __launch_bounds__(1024) k_get_head_fused_nvl(ghost_votes_args V, ghost_tree_args A, ghost_peer_args P, unsigned int* ticket,
+                                                              unsigned long long* local_votes, uint32_t* host_out, uint32_t host_seq) {
+    extern __shared__ unsigned long long smem_u64[];
+    __shared__ bool is_last;
+    ghost_votes_body(smem_u64, V.n, V.lmd_key, V.lmd_block, V.equiv, V.flags, V.eff, A.pre, A.n, local_votes, V.min_key, V.flag_need, V.flag_mask, A.dbg);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0;
+    const uint32_t par = P.seq & 1u, n = A.n;
+    // push: this rank's direct votes into every rank's accumulator (own included); the local vector is left clean for the next call
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long w = __ldcg(local_votes + i);
+        if (w) {
+            local_votes[i] = 0;
+            for (uint32_t r = 0; r < P.world; r++) atomicAdd(P.acc[r] + (size_t)par * n + i, w);      // RED.ADD.64 over NVLink for r != rank
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < P.world) {
+        // raise my flag on rank `threadIdx.x`, then wait for that rank's flag in my own row
+        volatile unsigned int* theirs = P.flags[threadIdx.x] + par * B2_MAX_PEERS + P.rank;
+        *theirs = P.seq;
+        volatile unsigned int* mine = P.flags[P.rank] + par * B2_MAX_PEERS + threadIdx.x;
+        while (*mine != P.seq) {
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    A.votes = P.acc[P.rank] + (size_t)par * n;         // the tree phase reads (ld.cg) and zeroes the complete accumulator
+    ghost_tree_smem(A, smem_u64, host_out, host_seq);
 }
 
 }  // namespace b2

@@ -280,6 +280,27 @@ class Engine:
         self._ck(self.lib.b2_get_head(self.h, int(justified_idx), int(boost_idx), int(boost_score), ctypes.byref(out)))
         return int(out.value)
 
+    # ------------------------------------------------------------------ multi-GPU get_head over NVLink peer memory
+    def fc_exchange_setup(self, rank: int, world: int, process_group=None):
+        """Map the vote-exchange blocks of all ranks of the box into this context (CUDA IPC handles all-gathered over `process_group`;
+        world == 1 needs no group).  Call after tree_load, on every rank."""
+        h = np.zeros(64, dtype=np.uint8)
+        self._ck(self.lib.b2_fc_exchange_export(self.h, _p(h)))
+        if world > 1:
+            import torch.distributed as dist
+            gathered = [None] * world
+            dist.all_gather_object(gathered, h.tobytes(), group=process_group)
+            allh = np.frombuffer(b"".join(gathered), dtype=np.uint8).copy()
+        else:
+            allh = h
+        self._ck(self.lib.b2_fc_exchange_open(self.h, int(rank), int(world), _p(allh)))
+
+    def get_head_multi(self, v_begin: int, v_end: int, justified_idx: int = 0, boost_idx: int = -1, boost_score: int = 0) -> int:
+        """COLLECTIVE get_head: this rank scatters validators [v_begin, v_end); the all-reduce runs inside the kernel over NVLink."""
+        out = ctypes.c_uint32(0)
+        self._ck(self.lib.b2_get_head_multi(self.h, int(v_begin), int(v_end), int(justified_idx), int(boost_idx), int(boost_score), ctypes.byref(out)))
+        return int(out.value)
+
     def debug_head_clocks(self):
         """clock64 stamps of the phases of the last get_head (profiling aid) -> uint64[32]"""
         out = np.zeros(32, dtype=np.uint64)

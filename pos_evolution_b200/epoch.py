@@ -153,9 +153,30 @@ class EpochProcessor:
             torch.distributed.all_reduce(self.d_votes, group=self.pg)
         e.head_from_votes_dev(self.d_votes, self.d_head[slot], justified_idx, boost_idx, boost_score)
 
-    def get_head(self, justified_idx=0, boost_idx=-1, boost_score=0):
-        """get_head over the current LMD table through the multi-rank path (vote scatter of this rank's validators,
-        all-reduce, head on every rank); returns the head index on the host.  What bench.py times as get_head at N > 1."""
+    def enable_fused_get_head(self):
+        """Sharded mode: set up get_head as ONE kernel per rank with the vote all-reduce fused in over NVLink peer memory
+        (Engine.fc_exchange_setup: CUDA IPC handles exchanged over the process group).  Call on every rank, after tree_load."""
+        assert self.sharded, "the fused multi-GPU get_head is for a validator set sharded over the ranks"
+        ok, why = 1, ""
+        try:
+            self.eng.fc_exchange_setup(self.rank, self.world, self.pg)
+        except Exception as e:                        # e.g. CUDA IPC not permitted between the processes of this box
+            ok, why = 0, repr(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=self.pg)      # all ranks or none: the call is collective
+        self._fused_head = bool(int(flag.item()))
+        self.fused_head_error = why
+        return self._fused_head
+
+    def get_head(self, justified_idx=0, boost_idx=-1, boost_score=0, fused=None):
+        """get_head over the current LMD table through the multi-rank path; returns the head index on the host.  COLLECTIVE.
+        fused (default: whether enable_fused_get_head was called): one kernel per rank -- vote scatter of this rank's validators,
+        64-bit reductions into every rank's accumulator over NVLink, flag exchange, tree phase, zero-copy result.  Otherwise the
+        three-stage form: scatter kernel, NCCL all-reduce of u64[n_blocks], tree kernel, device-to-host copy."""
+        if fused is None:
+            fused = getattr(self, "_fused_head", False)
+        if fused:
+            return self.eng.get_head_multi(self.v0, self.v1, justified_idx, boost_idx, boost_score)
         self._fork_choice(0, justified_idx, boost_idx, boost_score)
         return int(self.d_head[0].item())
 

@@ -208,3 +208,42 @@ def test_attestations_wire_decode_matches_oracle(eng):
         row = np.unpackbits(bits[a], bitorder="little")
         assert [bool(x) for x in row[:len(wbits)]] == wbits and not row[len(wbits):].any(), a
         assert data[a].tobytes() == wdata and sig[a].tobytes() == wsig, a
+
+
+@pytest.mark.parametrize("n_val,n_blk,seed", [(5000, 300, 4), (1 << 20, 10000, 4), (70000, 14000, 6)])
+def test_get_head_forms_agree(eng, n_val, n_blk, seed):
+    """The forms of get_head give the oracle's head: the one-launch kernel (b2_get_head, default), the two-launch form (a context
+    created with B2_HEAD_FUSED=0), the NVLink-fused multi-rank kernel on a box of one rank (b2_get_head_multi, world = 1: scatter,
+    push into its own accumulator, flag exchange with itself, tree), also when only a validator range is scattered; repeated calls
+    (double-buffered accumulators, sequence numbers) stay correct; justified roots other than block 0 and the boost are honoured."""
+    import os
+    from pos_evolution_b200.engine import Engine
+    parent, slot, roots, leaf_viable = scenarios.fork_tree(n_blk, seed)
+    msg_block, has_msg, equiv, active, eff = scenarios.votes(n_val, n_blk, seed)
+    keep = fast.ghost_viable(parent, leaf_viable)
+    boost = fast.proposer_boost_score(eff, active, 32, 40)
+    os.environ["B2_HEAD_FUSED"] = "0"
+    try:
+        eng2 = Engine(0)
+    finally:
+        del os.environ["B2_HEAD_FUSED"]
+    for e in (eng, eng2):
+        _registry(e, n_val, eff, active)
+        e.tree_load(parent, slot, roots, leaf_viable)
+        e.latest_messages_load(np.full(n_val, 3, dtype=np.uint64), msg_block, has_msg, equiv)
+    eng.fc_exchange_setup(0, 1)
+    for justified, boost_idx in ((0, -1), (0, n_blk - 1), (n_blk // 3, n_blk // 2), (0, -1)):
+        w = fast.ghost_weights(parent, msg_block, has_msg, eff, active, equiv, boost_idx, boost)
+        want = fast.ghost_head(parent, roots, keep, w, justified)
+        for rep in range(3):
+            assert eng.get_head(justified, boost_idx, boost) == want
+            assert eng2.get_head(justified, boost_idx, boost) == want
+            assert eng.get_head_multi(0, n_val, justified, boost_idx, boost) == want
+    # a validator range only: the head of the sub-population
+    lo, hi = n_val // 4, n_val // 2
+    sub = np.zeros(n_val, dtype=np.uint8)
+    sub[lo:hi] = has_msg[lo:hi]
+    w = fast.ghost_weights(parent, msg_block, sub, eff, active, equiv, -1, 0)
+    assert eng.get_head_multi(lo, hi, 0, -1, 0) == fast.ghost_head(parent, roots, keep, w, 0)
+    assert eng.get_head(0, -1, 0) == fast.ghost_head(parent, roots, keep, fast.ghost_weights(parent, msg_block, has_msg, eff, active, equiv, -1, 0), 0)
+    eng2.close()

@@ -7,7 +7,8 @@ reports what it saw; the parent process compares EVERY rank with the single-proc
   * the all-gathered aggregate signatures == oracle.Sign(sum of the committee's secret keys, message) on a sample from each rank's share;
   * the replicated latest-message table after the last epoch == the sequential update_latest_messages of the numpy oracle;
   * the head of every epoch (vote scatter of N/world validators per rank -> all-reduce -> head) == the numpy oracle's get_head;
-  * EpochProcessor.get_head (the path bench.py times at N > 1) == the same head."""
+  * EpochProcessor.get_head (the path bench.py times at N > 1) == the same head, in its three-stage form (scatter, NCCL all-reduce,
+    tree) and in the one-kernel form with the all-reduce fused in over NVLink peer memory (b2_get_head_multi), repeatedly."""
 import hashlib
 import os
 import socket
@@ -70,9 +71,14 @@ def _worker(rank, world, port, q):
     agg = out[-1].aggregate_signatures().cpu().numpy()
     e, b, h = eng.latest_messages_read()
     lmd = hashlib.sha256(e[h == 1].tobytes() + b[h == 1].tobytes() + h.tobytes()).hexdigest()
-    head_again = ep.get_head(0, bench.N_BLOCKS - 1, W["boost"])
+    head_again = ep.get_head(0, bench.N_BLOCKS - 1, W["boost"])                       # scatter kernel -> NCCL all-reduce -> tree kernel
+    torch.cuda.synchronize()
+    assert ep.enable_fused_get_head(), ep.fused_head_error                            # CUDA IPC exchange blocks over NVLink
+    heads_fused = [ep.get_head(0, bench.N_BLOCKS - 1, W["boost"], fused=True) for _ in range(5)]   # one kernel per rank, all-reduce fused in
+    heads_fused.append(ep.get_head(0, -1, 0, fused=True))
+    heads_fused.append(ep.get_head(0, -1, 0, fused=False))
     sample = [a for a in (0, 511, 1023, 1024, 1100, 2046) if a not in bad]
-    q.put((rank, res, {a: bytes(agg[a]) for a in sample}, lmd, head_again, eng.guard_flags()))
+    q.put((rank, res, {a: bytes(agg[a]) for a in sample}, lmd, head_again, eng.guard_flags(), heads_fused))
     dist.barrier()
     dist.destroy_process_group()
     eng.close()
@@ -137,7 +143,10 @@ def test_sharded_epoch_on_two_gpus_equals_the_oracle():
         want_heads.append(fast.ghost_head(parent, roots, keep, w, 0))
     want_lmd = hashlib.sha256(m_epoch[has_msg == 1].tobytes() + msg_block[has_msg == 1].tobytes() + has_msg.tobytes()).hexdigest()
 
-    for rank, res, agg_sample, lmd, head_again, guard in results:
+    w_nb = fast.ghost_weights(parent, msg_block, has_msg, eff, active, equiv, -1, 0)
+    want_no_boost = fast.ghost_head(parent, roots, keep, w_nb, 0)
+    for rank, res, agg_sample, lmd, head_again, guard, heads_fused in results:
+        assert heads_fused == [want_heads[-1]] * 5 + [want_no_boost, want_no_boost], (rank, heads_fused)
         assert len(res) == N_EPOCHS and guard == 0
         for k, (okb, head) in enumerate(res):
             assert np.array_equal(np.frombuffer(okb, dtype=np.uint8), expect_ok), (rank, k)
