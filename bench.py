@@ -280,13 +280,22 @@ def run_gpu(args):
         pg = dist.group.WORLD
     strong = args.scaling == "strong"
     shard = (rank, world) if (strong and world > 1) else None
-    depth = args.depth or ({1: 3, 2: 4, 4: 6}.get(world, 8) if strong else 3)
+    if args.emulate_world > 1:                          # tuning aid: ONE rank's share of an epoch sharded over emulate_world ranks, no collectives
+        assert world == 1
+        shard = (0, args.emulate_world)
+    eff_world = args.emulate_world if args.emulate_world > 1 else world
+    # depth / how many epochs at the end of a batch take the short-latency tail: tuned on 1, 2 and 8 GPUs and with --emulate-world
+    # (profiles/r2c_sweep_*.json, r2d_emu_*.json)
+    depth_default, team_last_default = {1: (3, 1), 2: (4, 1), 4: (8, 3)}.get(eff_world, (12, 4)) if strong else (3, 1)
+    depth = args.depth or depth_default
     eng = Engine(local)
     if args.rlc:
         eng.set_verify_mode(True)                      # FastAggregateVerify in random-linear-combination batches (fresh os.urandom seed)
     W = build_world(eng, rank, np, PS, shard=shard)
-    ep = EpochProcessor(eng, N_AGG, N_VAL, COMMITTEE_SIZE // 8, N_BLOCKS, process_group=pg, device=dev, depth=depth, shard=shard, n_validators=N_VAL)
+    ep = EpochProcessor(eng, N_AGG, N_VAL, COMMITTEE_SIZE // 8, N_BLOCKS, process_group=pg, device=dev, depth=depth, shard=shard, n_validators=N_VAL,
+                        tail_form=args.tail_form)
     ep.set_committees(W["members"], W["off"])
+    ep.team_last = args.team_last if args.team_last is not None else team_last_default
     n_loc_sig = ep.n_sig_loc                                 # individual signatures this rank aggregates per step
     bits_np = np.full((N_AGG, COMMITTEE_SIZE // 8), 0xFF, dtype=np.uint8)
     blk_np = (N_BLOCKS - 1 - (np.arange(N_AGG) % 64)).astype(np.int32)
@@ -318,7 +327,7 @@ def run_gpu(args):
         results = []
         for i in range(n):
             d_epoch.add_(1)
-            t = ep.submit_dev(d_sigs, d_bits, d_msgs, d_epoch, d_blk, 0, boost_idx, boost, last=(i == n - 1))
+            t = ep.submit_dev(d_sigs, d_bits, d_msgs, d_epoch, d_blk, 0, boost_idx, boost, last=ep.drain_hint(n - 1 - i))
             if t is not None:
                 results.append(t)
         results.extend(ep.drain())
@@ -330,7 +339,7 @@ def run_gpu(args):
             host_epoch_counter[0] += 1
             he = h_epochs[host_epoch_counter[0] % len(h_epochs)]   # a pinned buffer is rewritten only after the epoch that read it has completed
             he.fill_(1000 + host_epoch_counter[0])
-            t = ep.submit_host(h_sigs, h_bits, h_msgs, he, h_blk, 0, boost_idx, boost, last=(i == n - 1))
+            t = ep.submit_host(h_sigs, h_bits, h_msgs, he, h_blk, 0, boost_idx, boost, last=ep.drain_hint(n - 1 - i))
             if t is not None:
                 results.append(t.wait())               # host blocks on the D2H of the epoch submitted depth-1 calls ago
         for t in ep.drain():
@@ -342,7 +351,8 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         ok, head = step_sync()
     barrier()
-    assert int(ok.sum().item()) == N_AGG, "GPU rejected valid aggregates"
+    n_expect = N_AGG if args.emulate_world <= 1 else ep.n_loc       # (an emulated rank sees only its own verdicts)
+    assert int(ok.sum().item()) == n_expect, "GPU rejected valid aggregates"
     head0 = int(head.item())
     if world > 1:
         hh = torch.tensor([head0, -head0], dtype=torch.int64, device=dev)
@@ -350,7 +360,7 @@ def run_gpu(args):
         assert int(hh[0]) == head0 and int(hh[1]) == -head0, "ranks disagree on the head"
     for t in run_pipelined_dev(depth):
         okp, headp = t.wait()
-        assert int(okp.sum().item()) == N_AGG and headp == head0, "pipelined epoch disagrees with the synchronous one"
+        assert int(okp.sum().item()) == n_expect and headp == head0, "pipelined epoch disagrees with the synchronous one"
     agg_sig_gpu = ep.d_agg_sig[(ep.k - 1) % depth].cpu().numpy()          # bls.Aggregate's result of the last epoch, all 2 048 committees
 
     # ---- synchronous form (one epoch at a time), for reference
@@ -380,14 +390,14 @@ def run_gpu(args):
     # ---- timed region 2: end to end through the public host API (pinned host buffers; H2D of every epoch's inputs and D2H of
     # its verdicts + head + aggregate signatures inside the region; copies of epoch k+1 overlap with the compute of epoch k)
     res = run_pipelined_host(depth)
-    assert all(int(o.sum()) == N_AGG for o, _ in res)
+    assert all(int(o.sum()) == n_expect for o, _ in res)
     barrier()
     ev0.record()
     res = run_pipelined_host(args.steps)
     ev1.record()
     barrier()
     ms_e2e = ev0.elapsed_time(ev1) / args.steps
-    assert len(res) == args.steps and all(int(o.sum()) == N_AGG and hd == res[0][1] for o, hd in res)
+    assert len(res) == args.steps and all(int(o.sum()) == n_expect and hd == res[0][1] for o, hd in res)
     assert np.array_equal(ep.h_agg_sig[(ep.k - 1) % depth].numpy(), agg_sig_gpu), "host copy of the aggregate signatures differs"
 
     # ---- dominant kernel alone (roofline): stage 1+2 of bls.Aggregate on this rank's signatures
@@ -616,6 +626,10 @@ def main():
     ap.add_argument("--depth", type=int, default=0, help="epochs in flight in the software pipeline (2..8); 0 = 3 on one GPU, 4/6/8 on 2/4/8 GPUs of a sharded epoch")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = ONE 2^20-validator epoch sharded by slot over the ranks (north_star configs 4/5); weak = an own epoch per rank")
+    ap.add_argument("--tail-form", default="auto", choices=["auto", "thread", "team"],
+                    help="pairing kernels of the pipelined epochs: thread per aggregate (fewest instructions), 3-lane teams (shortest critical path), auto")
+    ap.add_argument("--emulate-world", type=int, default=0, help="tuning aid (1 GPU): run rank 0's share of an epoch sharded over this many ranks, without collectives")
+    ap.add_argument("--team-last", type=int, default=None, help="how many epochs at the end of a batch take the team-form tail (default 1)")
     ap.add_argument("--rlc", action="store_true", help="FastAggregateVerify in random-linear-combination batches (b2_set_verify_mode 1)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the per-config numbers of BASELINE.json configs 2 and 3")
     ap.add_argument("--probe-overlap", action="store_true",

@@ -214,7 +214,7 @@ int b2_epoch_dev(b2_ctx* ctx, const uint8_t* d_sig96, const uint32_t* d_members,
  *                             before the tail of epoch k+1, whose LMD update waits for the vote scatter issued before it.
  * The latency-bound tails of epochs k, k-1, .. thereby overlap with each other and with the grid-filling signature decompression of
  * epoch k+1: under that contention one tail takes longer than one decompression, so depth 3 is what keeps the multiply pipe busy. */
-#define B2_EPOCH_SLOTS 8
+#define B2_EPOCH_SLOTS 16
 int b2_epoch_start_dev(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits,
                        uint32_t bits_stride, const uint8_t* d_msg32, uint32_t n_agg, uint64_t n_sig, int32_t* d_agg_status, void* stream);
 int b2_epoch_tail_dev(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,

@@ -37,7 +37,7 @@ struct vslot {
     uint64_t n_sig_tail = 0;                               // signatures of the epoch whose segment sums the tail still has to run
     bool segsum_pending = false;
     dbuf pkjac_r, rscal, sg_aff, sg_flag, f_g, gpass;      // RLC batch mode: [r]PK, r, per-group signature sums, group Miller values / verdicts
-    cudaEvent_t ev_join0 = nullptr, ev_join1 = nullptr, ev_seg = nullptr, ev_tail_done = nullptr, ev_fork = nullptr;
+    cudaEvent_t ev_join0 = nullptr, ev_join1 = nullptr, ev_seg = nullptr, ev_tail_done = nullptr, ev_fork = nullptr, ev_in = nullptr;
     cudaStream_t s_tail = nullptr;      // the slot's own tail stream: tails of consecutive epochs overlap each other
     // the slot's own side streams (hash-to-G2; pubkey aggregation + first Miller loop).  With ONE pair shared by all slots the
     // latency-bound side chains of consecutive epochs serialise (6 + 10 ms per epoch) -- invisible behind a 32 ms decompression,
@@ -49,6 +49,14 @@ struct b2_ctx {
     int device = 0;
     int n_sm = 148;
     cudaStream_t s_main = nullptr;
+    // pipelined epochs: the decompression kernels of consecutive epochs alternate between two streams, so the blocks of epoch k+1 fill
+    // the SMs that epoch k's last, partial wave leaves idle (a rank's share of a sharded epoch is 1.7 waves at N = 8: 5.04 ms instead of
+    // 3.65 ms per 131 072 signatures when the kernels run back to back on one stream)
+    cudaStream_t s_dec[2] = {nullptr, nullptr};
+    // Measured (profiles/r2d_emu_*): one rank's share at N = 8 / 4: 5.45 vs 5.97 and 9.75 vs 10.07 ms per epoch; at N = 1 (13.8 waves) the
+    // overlap costs 0.3 ms instead, so the alternation is used only for decompressions of fewer than 6 waves (B2_DEC_ALTERNATE=0/1 forces)
+    int dec_alternate = -1;                           // -1 auto, 0 never, 1 always
+    unsigned dec_turn = 0;
     cudaEvent_t ev_votes_done = nullptr, ev_lmd_done = nullptr;
     vslot slot[B2_EPOCH_SLOTS];
     char err[512] = {0};
@@ -200,6 +208,8 @@ int b2_init(int device, b2_ctx** out) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaError_t e = cudaStreamCreateWithPriority(&ctx->s_main, cudaStreamNonBlocking, prio_lo);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithPriority(&ctx->s_dec[i], cudaStreamNonBlocking, prio_lo);
+    if (const char* ev = getenv("B2_DEC_ALTERNATE")) ctx->dec_alternate = atoi(ev) != 0 ? 1 : 0;
     for (int i = 0; i < B2_EPOCH_SLOTS && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithPriority(&ctx->slot[i].s_tail, cudaStreamNonBlocking, prio_hi);
         for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaStreamCreateWithPriority(&ctx->slot[i].s_aux[k], cudaStreamNonBlocking, prio_hi);
@@ -207,8 +217,9 @@ int b2_init(int device, b2_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_lmd_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_votes_done, cudaEventDisableTiming);
     for (int i = 0; i < B2_EPOCH_SLOTS && e == cudaSuccess; i++) {
-        cudaEvent_t* evs[5] = {&ctx->slot[i].ev_join0, &ctx->slot[i].ev_join1, &ctx->slot[i].ev_seg, &ctx->slot[i].ev_tail_done, &ctx->slot[i].ev_fork};
-        for (int k = 0; k < 5 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(evs[k], cudaEventDisableTiming);
+        cudaEvent_t* evs[6] = {&ctx->slot[i].ev_join0, &ctx->slot[i].ev_join1, &ctx->slot[i].ev_seg, &ctx->slot[i].ev_tail_done, &ctx->slot[i].ev_fork,
+                               &ctx->slot[i].ev_in};
+        for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(evs[k], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_votes_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -305,7 +316,7 @@ void b2_destroy(b2_ctx* ctx) {
         dbuf* vb[] = {&V.haff, &V.hflag, &V.pkjac, &V.pkst, &V.saff, &V.sflag, &V.f, &V.sumjac, &V.pkjac_r, &V.rscal, &V.sg_aff, &V.sg_flag, &V.f_g, &V.gpass, &V.g2aff, &V.g2st};
         for (dbuf* b : vb)
             if (b->p) cudaFree(b->p);
-        cudaEvent_t evs[5] = {V.ev_join0, V.ev_join1, V.ev_seg, V.ev_tail_done, V.ev_fork};
+        cudaEvent_t evs[6] = {V.ev_join0, V.ev_join1, V.ev_seg, V.ev_tail_done, V.ev_fork, V.ev_in};
         for (cudaEvent_t ev : evs)
             if (ev) cudaEventDestroy(ev);
         if (V.s_tail) cudaStreamDestroy(V.s_tail);
@@ -313,6 +324,8 @@ void b2_destroy(b2_ctx* ctx) {
             if (V.s_aux[k]) cudaStreamDestroy(V.s_aux[k]);
     }
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    for (int i = 0; i < 2; i++)
+        if (ctx->s_dec[i]) cudaStreamDestroy(ctx->s_dec[i]);
     if (ctx->ev_lmd_done) cudaEventDestroy(ctx->ev_lmd_done);
     if (ctx->d_dec_counter) cudaFree(ctx->d_dec_counter);
     if (ctx->d_guard) cudaFree(ctx->d_guard);
@@ -640,7 +653,7 @@ static int verify_fork(b2_ctx* ctx, vslot& V, const pk_source& P, const uint8_t*
     CK(cudaStreamWaitEvent(V.s_aux[0], V.ev_fork, 0));
     CK(cudaStreamWaitEvent(V.s_aux[1], V.ev_fork, 0));
     const unsigned tb = team ? 32u : ctx->tail_block;
-    k_hash_to_g2<<<blocks_for(n_agg, tb), tb, 0, V.s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)V.haff.p, (uint8_t*)V.hflag.p);
+    k_hash_to_g2<<<blocks_for(2ull * n_agg, tb), tb, 0, V.s_aux[0]>>>(d_msg32, n_agg, (uint32_t*)V.haff.p, (uint8_t*)V.hflag.p);
     CKL(ctx);
     CK(cudaEventRecord(V.ev_join0, V.s_aux[0]));
     if (P.d_pk48) {
@@ -746,8 +759,15 @@ static int epoch_start(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint
     if ((rc = verify_fork(ctx, V, P, d_msg32, n_agg, s, team))) return rc;
     V.segsum_pending = own_buffers;
     V.n_sig_tail = n_sig;
-    if ((rc = aggregate_front(ctx, V, d_sig96, d_off, n_agg, n_sig, d_agg_status, s, team ? -1 : slot, own_buffers))) return rc;
-    CK(cudaEventRecord(V.ev_seg, s));
+    cudaStream_t sd = s;
+    const bool few_waves = n_sig < (uint64_t)6 * ctx->n_sm * 4 * ctx->dec_block;
+    if (own_buffers && (ctx->dec_alternate == 1 || (ctx->dec_alternate < 0 && few_waves))) {      // the slot's own point buffer makes this legal
+        sd = ctx->s_dec[ctx->dec_turn++ & 1u];
+        CK(cudaEventRecord(V.ev_in, s));                // inputs ready, slot drained
+        CK(cudaStreamWaitEvent(sd, V.ev_in, 0));
+    }
+    if ((rc = aggregate_front(ctx, V, d_sig96, d_off, n_agg, n_sig, d_agg_status, sd, team ? -1 : slot, own_buffers))) return rc;
+    CK(cudaEventRecord(V.ev_seg, sd));
     return B2_OK;
 }
 static int epoch_tail(b2_ctx* ctx, int slot, const uint32_t* d_members, const uint32_t* d_off, const uint8_t* d_bits, uint32_t bits_stride,
@@ -903,7 +923,7 @@ int b2_hash_to_g2(b2_ctx* ctx, const uint8_t* msg32, uint32_t n_msg, uint8_t* ou
         (rc = ensure(ctx, ctx->sc_hflag, n_msg)) || (rc = ensure(ctx, ctx->out_a, (size_t)n_msg * 96)))
         return rc;
     CK(cudaMemcpyAsync(ctx->in_e.p, msg32, (size_t)n_msg * 32, cudaMemcpyHostToDevice, s));
-    k_hash_to_g2<<<blocks_for(n_msg, 32), 32, 0, s>>>((const uint8_t*)ctx->in_e.p, n_msg, (uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->sc_hflag.p);
+    k_hash_to_g2<<<blocks_for(2ull * n_msg, 32), 32, 0, s>>>((const uint8_t*)ctx->in_e.p, n_msg, (uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->sc_hflag.p);
     CKL(ctx);
     k_g2_compress_aff<<<blocks_for(n_msg, 64), 64, 0, s>>>((const uint32_t*)ctx->sc_haff.p, (const uint8_t*)ctx->sc_hflag.p, n_msg, (uint8_t*)ctx->out_a.p);
     CKL(ctx);
@@ -925,7 +945,7 @@ int b2_sign(b2_ctx* ctx, const uint32_t* sk8, const uint32_t* msg_idx, uint64_t 
     CK(cudaMemcpyAsync(ctx->in_f.p, sk8, n * 32, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->in_g.p, msg_idx, n * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->in_e.p, msg32, (size_t)n_msg * 32, cudaMemcpyHostToDevice, s));
-    k_hash_to_g2<<<blocks_for(n_msg, 32), 32, 0, s>>>((const uint8_t*)ctx->in_e.p, n_msg, (uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->sc_hflag.p);
+    k_hash_to_g2<<<blocks_for(2ull * n_msg, 32), 32, 0, s>>>((const uint8_t*)ctx->in_e.p, n_msg, (uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->sc_hflag.p);
     CKL(ctx);
     k_sign<<<blocks_for(n, 64), 64, 0, s>>>((const uint32_t*)ctx->in_f.p, (const uint32_t*)ctx->in_g.p, n, (const uint32_t*)ctx->sc_haff.p, (uint8_t*)ctx->out_a.p);
     CKL(ctx);

@@ -267,12 +267,30 @@ __global__ void __launch_bounds__(128, B2_TAIL_MIN_BLOCKS) k_g2_finish(const uin
 }
 
 // ------------------------------------------------------------------------------------------ K4-K6: verification pipeline
+// Two lanes per message: hash_to_curve maps TWO field elements to the curve (RFC 9380 section 3: Q0 = map(u0), Q1 = map(u1)) with
+// three Fp exponentiations each, independent of one another -- the odd lane maps u1 while the even lane maps u0 and then takes Q1 over
+// by shuffle for the addition, the cofactor clearing and the affine conversion.  Same functions, same bytes as core_hash_msg; the
+// critical path of the kernel (one thread's instruction stream: 6.3 ms for 2 048 messages) loses one of its two SSWU maps.
 __global__ void __launch_bounds__(128, B2_TAIL_MIN_BLOCKS) k_hash_to_g2(const uint8_t* __restrict__ msg32, uint32_t n, uint32_t* h_aff, uint8_t* hflag) {
-    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t a = t >> 1, half = t & 1u;
+    const bool live = a < n;
+    g2_jac q = pt_inf<fp2>();
+    if (live) {
+        uint8_t dst[B2_DST_POP_LEN];
+#pragma unroll 1
+        for (int i = 0; i < B2_DST_POP_LEN; i++) dst[i] = dst_pop_byte(i);
+        fp2 u0, u1;
+        hash_to_field_fp2x2(msg32 + 32 * (uint64_t)a, 32, dst, B2_DST_POP_LEN, u0, u1);
+        q = map_to_curve_g2(half ? u1 : u0);
+    }
+    const g2_jac other = shfl_down_pod(q, 1);               // the odd lane's Q1 (whole warps execute this: blockDim is a multiple of 32)
+    if (!live || half) return;
+    q = g2_clear_cofactor(pt_add(q, other));
     g2_aff h;
-    uint8_t f;
-    core_hash_msg(msg32, a, h, f);
+    h.x = fp2_zero();
+    h.y = fp2_zero();
+    const uint8_t f = pt_to_affine(q, h) ? 0 : 1;
     uint32_t* o = h_aff + 48 * (uint64_t)a;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(&h);
 #pragma unroll
@@ -780,9 +798,11 @@ template <class T> __device__ __forceinline__ void smem_exclusive_scan(T* x, uin
     const uint32_t rows = ((n + 31) / 32 + nwarp - 1) / nwarp;            // rows of 32 per warp
     const uint32_t base = warp * rows * 32;
     T carry = 0;
-    // eight rows at a time: their shuffle scans are independent chains the scheduler interleaves (a u64 shuffle step is two dependent
-    // SHFLs of ~25 cycles; row after row that chain was 6 600 clocks for 10 000 elements, profiles/r2_head_clocks_v2.jsonl)
-    constexpr int G = 8;
+    // two rows at a time: their shuffle scans are independent chains the scheduler interleaves.  More does not help: the 32 warps of the
+    // block share ONE shuffle unit (32 lanes per clock), so 313 rows x 5 steps x 2 SHFL (u64) = 3 100 clocks is the floor of this
+    // formulation; eight rows at a time was SLOWER (9 400 vs 6 600 clocks: the padding rows of the last group still shuffle, and the
+    // 64-register cap of a 1 024-thread block spills), profiles/r2_head_clocks_v2.jsonl / _v3.jsonl
+    constexpr int G = 2;
     for (uint32_t r0 = 0; r0 < rows; r0 += G) {
         T v[G], incl[G];
 #pragma unroll

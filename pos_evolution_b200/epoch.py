@@ -33,7 +33,7 @@ import torch
 
 from .engine import Engine
 
-MAX_DEPTH = 8       # == B2_EPOCH_SLOTS (include/b200pos.h)
+MAX_DEPTH = 16      # == B2_EPOCH_SLOTS (include/b200pos.h)
 
 
 class _Ticket:
@@ -111,7 +111,12 @@ class EpochProcessor:
         self._inflight = collections.deque()      # tickets of the submitted, not yet returned epochs
         self._team_form = False
         assert tail_form in ("auto", "thread", "team")
-        self.always_team = tail_form == "team" or (tail_form == "auto" and self.n_loc <= 1024)
+        # Measured on 2 and 8 GPUs (profiles/r2c_sweep_*.json): the thread-per-aggregate tail wins at every N as long as enough epochs are
+        # in flight to cover its latency (N = 2: 18.5 ms thread / depth 4 against 21.7 ms team; N = 8: 6.32 against 6.80) -- the one-warp
+        # team blocks with their 49 KB of shared memory displace more decompression blocks than their shorter latency is worth.
+        self.always_team = tail_form == "team"
+        # ... except at the end of a batch: the last `team_last` epochs take the team form (see drain_hint)
+        self.team_last = 1
 
     def set_committees(self, members, off):
         """members u32[n_sig] (committee order), off u32[n_agg+1] for the WHOLE epoch; signature j belongs to member j."""
@@ -138,7 +143,10 @@ class EpochProcessor:
         update_latest_messages for ALL accepted aggregates of the epoch on this rank's replica of the LMD table."""
         n = self.n_loc
         loc, allr = self.d_out_loc[slot], self.d_out_all[slot]
-        torch.distributed.all_gather_into_tensor(allr.view(-1), loc, group=self.pg)
+        if self.pg is None:                           # one rank of a sharded epoch on its own (bench.py --emulate-world): no peers to gather from
+            allr[self.rank].copy_(loc)
+        else:
+            torch.distributed.all_gather_into_tensor(allr.view(-1), loc, group=self.pg)
         self.d_agg_sig[slot].view(self.world, n * 96).copy_(allr[:, :n * 96])
         self.d_ok[slot].view(self.world, n).copy_(allr[:, n * 96:])
         self.eng.latest_messages_update_dev(self.d_members, self.d_off, d_bits, d_target_epoch, d_block_idx, self.d_ok[slot])
@@ -259,6 +267,11 @@ class EpochProcessor:
         if self.ev_fc[slot] is not None:
             stream.wait_event(self.ev_fc[slot])
         return slot
+
+    def drain_hint(self, remaining: int) -> bool:
+        """True when an epoch with `remaining` epochs still to come after it should take the short-latency (team) tail: the last epochs
+        of a batch cannot hide a thread-form tail (≈ 30 ms) behind decompressions that are no longer coming."""
+        return remaining < self.team_last
 
     def submit_dev(self, d_sigs, d_bits, d_msgs, d_target_epoch, d_block_idx, justified_idx=0, boost_idx=-1, boost_score=0, last=False):
         """Enqueue one epoch (device-resident inputs, which must stay untouched until its ticket has been waited for; d_sigs =

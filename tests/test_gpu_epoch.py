@@ -72,7 +72,7 @@ def _expected(pks, members, off, msgs, bits, sigs):
     return aggs, oks
 
 
-@pytest.mark.parametrize("mode,depth", [("sync", 3), ("pipelined", 2), ("pipelined", 3), ("pipelined", 4), ("pipelined", 8), ("pipelined_host", 3),
+@pytest.mark.parametrize("mode,depth", [("sync", 3), ("pipelined", 2), ("pipelined", 3), ("pipelined", 4), ("pipelined", 8), ("pipelined", 12), ("pipelined_host", 3),
                                         ("pipelined_host", 2), ("sync_host", 3), ("pipelined_team", 6), ("sync_rlc", 3), ("pipelined_rlc", 3),
                                         ("pipelined_host_rlc", 4)])
 def test_epoch_pipeline_matches_oracle(mode, depth):
