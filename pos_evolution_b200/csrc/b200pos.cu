@@ -223,6 +223,7 @@ int b2_init(int device, b2_ctx** out) {
     }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ghost_votes_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_g2_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, 432 * 128);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_g1_gather_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)sizeof(gather_ws));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_g1_gather_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)sizeof(gather_ws));
     ctx->n_sm = prop.multiProcessorCount;
@@ -535,7 +536,7 @@ static int aggregate_front(b2_ctx* ctx, vslot& V, const uint8_t* d_sig96, const 
         k_g2_decompress_persistent<<<ctx->n_sm * 4, 128, 0, s>>>(d_sig96, n_sig, (uint32_t*)aff.p, (uint8_t*)st.p, ctr, ctx->reserved);
         CKL(ctx);
     } else if (n_sig) {
-        k_g2_decompress<<<blocks_for(n_sig, ctx->dec_block), ctx->dec_block, ctx->pow_smem ? 384 * ctx->dec_block : 0, s>>>(
+        k_g2_decompress<<<blocks_for(n_sig, ctx->dec_block), ctx->dec_block, ctx->pow_smem ? 432 * ctx->dec_block : 0, s>>>(
             d_sig96, n_sig, (uint32_t*)aff.p, (uint8_t*)st.p, ctx->pow_smem ? 1 : 0);
         CKL(ctx);
     }

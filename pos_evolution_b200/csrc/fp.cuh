@@ -314,14 +314,15 @@ HD fp fp_mul8(const fp& a) { return fp_dbl(fp_mul4(a)); }
 
 // a^e for a fixed exponent given as a sliding-window schedule in the constant table (tools/gen_consts.py:
 // word 0 = number of steps, then (n_squarings << 8 | table index), index 255 = squarings only; window 4, table of the
-// eight odd powers a^1..a^15).  The schedule is the same in every thread, so nothing diverges.  For (p-3)/4 this is
-// 379 squarings + 76 multiplications + 8 for the table (the fixed-window version needed 380 + 92 + 14).
+// eight odd powers a^1..a^15 plus a^255).  The schedule is the same in every thread, so nothing diverges.  For (p-3)/4 this is
+// 380 squarings + 76 multiplications in all (375 + 68 in the schedule, 1 + 7 for the odd powers, 4 + 1 for a^255); the plain
+// window-4 parse of round 1 needed 376 + 85, the fixed-window version 380 + 106.
 // Where the eight odd powers live.  pow_tbl_local: a per-thread array -- dynamically indexed, so the compiler puts it in LOCAL memory
 // (384 B per thread; with 16 resident warps per SM these tables overflow L1 and their evicted lines are what made k_g2_decompress
 // write 1.2 GB to DRAM per launch, profiles/r1c_g2_decompress_raw.csv).  pow_tbl_strided: caller-provided SHARED memory, word (i, limb) of
 // thread t at base[(12 i + limb) * stride + t]: conflict-free, never leaves the SM.
 struct pow_tbl_local {
-    fp t[8];
+    fp t[9];
     HD void set(int i, const fp& v) { t[i] = v; }
     HD fp get(uint32_t i) const { return t[i]; }
 };
@@ -349,6 +350,14 @@ template <class TBL> HDN fp fp_pow_prog_t(const fp& a, int off, TBL& tbl) {
         cur = fp_mul(cur, a2);
         tbl.set(i, cur);
     }
+    // entry 8 = a^255 = (a^15)^16 * a^15: the run token of tools/gen_consts.py:token_program (one multiplication per EIGHT
+    // consecutive one-bits of the exponent instead of one per four; (p-3)/4 has runs of 33, 19, 17, 10, 8 and 6)
+    {
+        fp t = cur;
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) t = fp_sqr(t);
+        tbl.set(8, fp_mul(t, cur));
+    }
     const uint32_t n = prog[0];
     fp r = tbl.get(prog[1] & 0xffu);
 #pragma unroll 1
@@ -361,7 +370,7 @@ template <class TBL> HDN fp fp_pow_prog_t(const fp& a, int off, TBL& tbl) {
     }
     return r;
 }
-// tab == nullptr: table in a per-thread array; else 96 words per thread in shared memory at tab[(12 i + limb) * tab_stride]
+// tab == nullptr: table in a per-thread array; else 108 words per thread (nine entries) in shared memory at tab[(12 i + limb) * tab_stride]
 HD fp fp_pow_prog(const fp& a, int off, uint32_t* tab = nullptr, uint32_t tab_stride = 0) {
     if (tab) {
         pow_tbl_strided t = {tab, tab_stride};

@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(128) k_g1_segment_sum(const uint32_t* __restri
 
 // ------------------------------------------------------------------------------------------ K3: bls.Aggregate
 // stage 1: one thread per signature: ZCash decode + Fp2 square root (two Fp exponentiations) -> affine point
-// use_smem != 0: the sliding-window tables of the two exponentiations live in dynamic shared memory (96 words per thread, launch with
-// 384 B * blockDim.x) instead of local memory -- see pow_tbl_strided in fp.cuh
+// use_smem != 0: the sliding-window tables of the two exponentiations live in dynamic shared memory (108 words per thread, launch with
+// 432 B * blockDim.x) instead of local memory -- see pow_tbl_strided in fp.cuh
 __global__ void __launch_bounds__(128, 4) k_g2_decompress(const uint8_t* __restrict__ sig96, uint64_t n, uint32_t* aff_out, uint8_t* st_out, int use_smem) {
     extern __shared__ uint32_t pow_tab[];
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -52,7 +52,8 @@ int main() {
     cudaMalloc(&d_st, cand);
     cudaMalloc(&d_aff, cand * 192);
     cudaMemcpy(d_sig, h.data(), cand * 96, cudaMemcpyHostToDevice);
-    const size_t smem = VARIANT == 1 ? 384 * 128 : 0;
+    const size_t smem = VARIANT == 1 ? 432 * 128 : 0;
+    if (smem) cudaFuncSetAttribute(k_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_dec<<<(unsigned)((cand + 127) / 128), 128, smem>>>(d_sig, cand, d_aff, d_st);
     std::vector<uint8_t> st(cand);
     cudaMemcpy(st.data(), d_st, cand, cudaMemcpyDeviceToHost);

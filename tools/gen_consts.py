@@ -105,6 +105,51 @@ def sliding_window_program(e, w=4):
     return ops
 
 
+RUN_TOKEN = 255         # a^(2^8 - 1): table entry 8 of fp_pow_prog (built from a^15 with 4 squarings + 1 multiplication)
+
+
+def token_program(e, w=4):
+    """Constant-exponent schedule over the token set {odd values < 2^w} + {RUN_TOKEN}, parsed optimally (fewest multiplications) by
+    dynamic programming over the bit string.  (p-3)/4 has runs of 33, 19, 17, 10, 8 and 6 one-bits: a window-4 parse spends one
+    multiplication per four of them, the a^255 entry one per eight -- 68 instead of 78 multiplications for 5 extra operations.
+    Same output format as sliding_window_program; table index 8 = RUN_TOKEN."""
+    bits = bin(e)[2:]
+    n = len(bits)
+    toks = {bin(v)[2:]: (v - 1) // 2 for v in range(1, 1 << w, 2)}
+    toks[bin(RUN_TOKEN)[2:]] = 1 << (w - 1)
+    INF = 10**9
+    best, choice = [INF] * (n + 1), [None] * (n + 1)
+    best[n] = 0
+    for i in range(n - 1, -1, -1):
+        if bits[i] == "0":
+            best[i] = best[i + 1]
+            continue
+        for pat in toks:
+            if bits.startswith(pat, i) and 1 + best[i + len(pat)] < best[i]:
+                best[i], choice[i] = 1 + best[i + len(pat)], pat
+    ops, i, pending, first = [], 0, 0, True
+    while i < n:
+        if choice[i] is None:
+            pending += 1
+            i += 1
+            continue
+        pat = choice[i]
+        ops.append((0 if first else pending + len(pat), toks[pat]))
+        first, pending, i = False, 0, i + len(pat)
+    if pending:
+        ops.append((pending, 255))
+    a = 0x1234567
+    tbl = [pow(a, 2 * k + 1, P) for k in range(1 << (w - 1))] + [pow(a, RUN_TOKEN, P)]
+    r = tbl[ops[0][1]]
+    for nsq, idx in ops[1:]:
+        for _ in range(nsq):
+            r = r * r % P
+        if idx != 255:
+            r = r * tbl[idx] % P
+    assert r == pow(a, e, P)
+    return ops
+
+
 def build():
     """-> ordered list of (name, kind, value); kind in {'fp','fp2','raw'}; raw = not Montgomery."""
     c = []
@@ -119,7 +164,8 @@ def build():
     raw("C_EXP_PM2", P - 2)                                 # Fermat inverse
     raw("C_R_ORDER", R_ORDER)                               # subgroup order, 255 bits (top limbs zero)
     for name, e in (("C_PROG_PM3D4", (P - 3) // 4), ("C_PROG_PM2", P - 2)):
-        ops = sliding_window_program(e, 4)
+        ops = token_program(e, 4)
+        assert len(ops) <= len(sliding_window_program(e, 4))
         c.append((name, "words", [len(ops)] + [(nsq << 8) | idx for nsq, idx in ops]))
     fp("C_ONE", 1)
     fp("C_TWO_INV", pow(2, -1, P))

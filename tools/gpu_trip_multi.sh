@@ -7,9 +7,6 @@ mkdir -p gpurun_out
 export CUDA_DEVICE_MAX_CONNECTIONS=32
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 if [ "$N" -le 2 ]; then
-  echo "== single-GPU suite"; timeout 1500 python -m pytest tests -x -q -m gpu --deselect tests/test_gpu_multirank.py 2>&1 | tail -5
-  echo "== head clocks"; timeout 300 python tools/head_clocks.py | tee -a gpurun_out/head_clocks4.jsonl
-  echo "== imad / tensor-core concurrency"; timeout 120 tools/mma_pipe_microbench.bin | tee gpurun_out/mma_pipe_microbench.jsonl
   echo "== multirank parity test"; timeout 900 python -m pytest tests/test_gpu_multirank.py -x -q -m gpu 2>&1 | tail -8
 fi
 echo "== bench strong N=$N"
