@@ -52,7 +52,8 @@ struct b2_ctx {
     // pipelined epochs: the decompression kernels of consecutive epochs alternate between two streams, so the blocks of epoch k+1 fill
     // the SMs that epoch k's last, partial wave leaves idle (a rank's share of a sharded epoch is 1.7 waves at N = 8: 5.04 ms instead of
     // 3.65 ms per 131 072 signatures when the kernels run back to back on one stream)
-    cudaStream_t s_dec[2] = {nullptr, nullptr};
+    cudaStream_t s_dec[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned n_dec_streams = 2;                       // B2_DEC_STREAMS (2..4)
     // Measured (profiles/r2d_emu_*): one rank's share at N = 8 / 4: 5.45 vs 5.97 and 9.75 vs 10.07 ms per epoch; at N = 1 (13.8 waves) the
     // overlap costs 0.3 ms instead, so the alternation is used only for decompressions of fewer than 6 waves (B2_DEC_ALTERNATE=0/1 forces)
     int dec_alternate = -1;                           // -1 auto, 0 never, 1 always
@@ -208,7 +209,11 @@ int b2_init(int device, b2_ctx** out) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaError_t e = cudaStreamCreateWithPriority(&ctx->s_main, cudaStreamNonBlocking, prio_lo);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithPriority(&ctx->s_dec[i], cudaStreamNonBlocking, prio_lo);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaStreamCreateWithPriority(&ctx->s_dec[i], cudaStreamNonBlocking, prio_lo);
+    if (const char* ev = getenv("B2_DEC_STREAMS")) {
+        unsigned v = (unsigned)atoi(ev);
+        if (v >= 2 && v <= 4) ctx->n_dec_streams = v;
+    }
     if (const char* ev = getenv("B2_DEC_ALTERNATE")) ctx->dec_alternate = atoi(ev) != 0 ? 1 : 0;
     for (int i = 0; i < B2_EPOCH_SLOTS && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithPriority(&ctx->slot[i].s_tail, cudaStreamNonBlocking, prio_hi);
@@ -325,7 +330,7 @@ void b2_destroy(b2_ctx* ctx) {
             if (V.s_aux[k]) cudaStreamDestroy(V.s_aux[k]);
     }
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 4; i++)
         if (ctx->s_dec[i]) cudaStreamDestroy(ctx->s_dec[i]);
     if (ctx->ev_lmd_done) cudaEventDestroy(ctx->ev_lmd_done);
     if (ctx->d_dec_counter) cudaFree(ctx->d_dec_counter);
@@ -763,7 +768,7 @@ static int epoch_start(b2_ctx* ctx, int slot, const uint8_t* d_sig96, const uint
     cudaStream_t sd = s;
     const bool few_waves = n_sig < (uint64_t)6 * ctx->n_sm * 4 * ctx->dec_block;
     if (own_buffers && (ctx->dec_alternate == 1 || (ctx->dec_alternate < 0 && few_waves))) {      // the slot's own point buffer makes this legal
-        sd = ctx->s_dec[ctx->dec_turn++ & 1u];
+        sd = ctx->s_dec[ctx->dec_turn++ % ctx->n_dec_streams];
         CK(cudaEventRecord(V.ev_in, s));                // inputs ready, slot drained
         CK(cudaStreamWaitEvent(sd, V.ev_in, 0));
     }
