@@ -24,6 +24,9 @@ for tma in (True, False):
     eng.gather_probe_dev(d_m, d_o, d_b, chk, tma=tma)
     torch.cuda.synchronize()
 out, st = eng.g1_aggregate(W["members"], W["off"], np.full((bench.N_AGG, 64), 0xFF, dtype=np.uint8))
+ok = eng.fast_aggregate_verify(W["members"][:64 * 512], W["off"][:65], np.full((64, 64), 0xFF, dtype=np.uint8), W["msgs"][:64],
+                               eng.aggregate(W["sigs"][:64 * 512], W["off"][:65])[0])
+assert ok.all()
 for _ in range(3):
     eng.get_head(0, bench.N_BLOCKS - 1, W["boost"])
 print("done")
