@@ -9,7 +9,7 @@ One call processes a whole epoch of attestations:
 
 Two ways to drive it:
   * `process_epoch_dev` / `process_epoch_host`: synchronous in stream order, one epoch at a time;
-  * `submit_dev` / `submit_host` + `drain`: software-pipelined over `depth` slots (default 3, at most B2_EPOCH_SLOTS = 8).
+  * `submit_dev` / `submit_host` + `drain`: software-pipelined over `depth` slots (default 3, at most B2_EPOCH_SLOTS = 16).
     The signature decompression of epoch k+1 (grid-filling, integer-pipe bound) overlaps with the latency-bound tails of
     the epochs before it (subgroup check, second Miller loop, final exponentiation, LMD update; each on its slot's own
     high-priority streams inside the library) and with their fork choice (on this object's fork-choice stream); in the
@@ -60,9 +60,9 @@ class EpochProcessor:
     def __init__(self, engine: Engine, n_agg: int, n_sig: int, bits_stride: int, n_blocks: int, process_group=None, device=None, depth: int = 3,
                  shard=None, n_validators=None, tail_form: str = "auto"):
         """n_agg / n_sig: aggregates and individual signatures of the WHOLE epoch (in sharded mode this rank handles 1/world of
-        them).  tail_form: "thread" (fewest instructions), "team" (shortest critical path) or "auto" (team when this rank's
-        share of an epoch is at most 1024 aggregates: the work per rank is then so short that latency, not multiply-pipe
-        time, decides how many epochs must be in flight)."""
+        them).  tail_form: "thread" (fewest instructions and smallest footprint; needs depth x step > the ~30-40 ms a tail lasts),
+        "team" (three lanes per pairing: shortest critical path) or "auto" (= thread: measured best at 1, 2, 4 and 8 GPUs, see
+        DESIGN.md section 6b).  Independently of it the last `team_last` epochs of a batch take the team form (drain_hint)."""
         self.eng = engine
         self.dev = device if device is not None else torch.device("cuda", engine.device)
         self.pg = process_group
