@@ -533,10 +533,10 @@ def run_gpu(args):
         algo_bytes = 96 * n_loc_sig + 96 * ep.n_loc                        # bls.Aggregate = 96n + 96s (this rank's share)
         achieved = algo_bytes / (ms_agg * 1e-3) / 1e9
         # integer-pipe reading of the same launch: IMAD.WIDE.U32 instructions per signature, counted from the SASS of fp_sqr (222)
-        # and fp_mul (288): 2 exponentiations x (379 squarings + 84 multiplications) + ~60 multiplications for the curve
-        # equation, sign fix and the segment additions.  Peak = 32 wide MACs / clk / SM (one IMAD.WIDE per 4 cycles per scheduler,
+        # and fp_mul (288): 2 exponentiations x (380 squarings + 76 multiplications: the schedule with the a^255 run token,
+        # tools/gen_consts.py) + ~60 multiplications for the curve equation, sign fix and the segment additions.  Peak = 32 wide MACs / clk / SM (one IMAD.WIDE per 4 cycles per scheduler,
         # ncu: sm__pipe_fmaheavy) x SMs x the SM clock sampled during the timed region.
-        wide_per_sig = 2 * (379 * 222 + 84 * 288) + 60 * 288
+        wide_per_sig = 2 * (380 * 222 + 76 * 288) + 60 * 288
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         int_peak = 32.0 * n_sm * sm_mhz * 1e6
