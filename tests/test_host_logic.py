@@ -348,3 +348,12 @@ def test_get_unslashed_participating_indices_matches_oracle():
         for epoch in (ospec.get_previous_epoch(ostate), ospec.get_current_epoch(ostate)):
             assert ps.get_unslashed_participating_indices(pstate, flag, epoch) == ospec.get_unslashed_participating_indices(ostate, flag, epoch)
     assert PS.Spec.has_flag(0b101, 2) and not PS.Spec.has_flag(0b101, 1) and PS.Spec.add_flag(0b001, 2) == 0b101
+
+
+def test_generated_constants_are_current():
+    """csrc/consts.cuh (field constants, Frobenius coefficients, the exponent schedules with their run token) is exactly what
+    tools/gen_consts.py renders: the generator self-checks every schedule against pow() when it builds them."""
+    import subprocess
+    import sys
+    rc = subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_consts.py"), "--check"])
+    assert rc == 0, "pos_evolution_b200/csrc/consts.cuh is stale: run python tools/gen_consts.py"
