@@ -911,31 +911,32 @@ __device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsign
     // parents thread by thread makes every warp wait for its lane with the most children in each of its ~10 trips (13 800 clocks).
     // When the launch left room for a work list (A.hard_list), the parents that need the loops are first compacted into it and
     // then spread evenly over the block.
+    // One traversal per parent (the child chain c -> c + size[c] is a chain of dependent shared-memory loads): every child is marked as
+    // it is visited, the best one is remembered and un-marked at the end -- two more shared atomics per parent instead of a second walk.
     auto mark_children = [&](uint32_t p, uint32_t sk) {
         const uint32_t end = p + B2_SZ(sk);
-        uint32_t best = 0xffffffffu, best_rk = 0;
-        if (B2_KEEP(sk)) {
-            unsigned long long bw = 0;
-            for (uint32_t c = p + 1; c < end;) {
-                const uint32_t sc = sz[c];
-                if (B2_KEEP(sc)) {
-                    const unsigned long long w = W[c];
-                    if (best == 0xffffffffu || w > bw || (w == bw && B2_RK(sc) > best_rk)) {
-                        best = c;
-                        bw = w;
-                        best_rk = B2_RK(sc);
-                    }
-                }
-                c += B2_SZ(sc);
-            }
-        }
+        const bool pick = B2_KEEP(sk) != 0;             // a block outside the filtered tree has no best child
+        uint32_t best = 0xffffffffu, best_rk = 0, best_step = 0;
+        unsigned long long bw = 0;
         for (uint32_t c = p + 1; c < end;) {
-            const uint32_t step = B2_SZ(sz[c]);
-            if (c != best) {
-                atomicAdd(&mark[c], 1u);
-                atomicAdd(&mark[c + step], 0xffffffffu);                    // -1 (mod 2^32); position n is the sentinel slot
+            const uint32_t sc = sz[c];
+            const uint32_t step = B2_SZ(sc);
+            atomicAdd(&mark[c], 1u);
+            atomicAdd(&mark[c + step], 0xffffffffu);                        // -1 (mod 2^32); position n is the sentinel slot
+            if (pick && B2_KEEP(sc)) {
+                const unsigned long long w = W[c];
+                if (best == 0xffffffffu || w > bw || (w == bw && B2_RK(sc) > best_rk)) {
+                    best = c;
+                    bw = w;
+                    best_rk = B2_RK(sc);
+                    best_step = step;
+                }
             }
             c += step;
+        }
+        if (best != 0xffffffffu) {
+            atomicAdd(&mark[best], 0xffffffffu);
+            atomicAdd(&mark[best + best_step], 1u);
         }
     };
     if (A.hard_list) {
