@@ -787,47 +787,36 @@ __device__ __forceinline__ void ghost_tree_body(const ghost_tree_args& A, unsign
 // 6 100): (1) all arrays are __shared__ pointers -- LDS/STS instead of generic LD/ST whose address space is resolved at run time;
 // (2) the per-block word packs subtree size, root rank and the filter bit, so a tie between equal-weight siblings costs no global
 // load (the generic body reads A.rank[] from global memory inside the child loop); (3) the staging loop issues all of a thread's
-// global loads before using any; (4) the prefix sums are row-wise warp scans (lane-contiguous: no bank conflicts) with one
-// cross-warp step; (5) the head and its sequence number leave in ONE 64-bit store to mapped host memory.
+// global loads before using any; (4) the prefix sums are raking scans (registers, one warp scan per warp, one cross-warp
+// step); (5) the head and its sequence number leave in ONE 64-bit store to mapped host memory.
 #define B2_SZ(x) ((x) & 0x7fffu)
 #define B2_RK(x) (((x) >> 15) & 0x7fffu)
 #define B2_KEEP(x) ((x) >> 31)
-// exclusive prefix sum of x[0..n) in shared memory, x[n] = total.  Warp w owns the contiguous rows [w*rows, (w+1)*rows) of 32 elements.
-template <class T> __device__ __forceinline__ void smem_exclusive_scan(T* x, uint32_t n, T* warp_tot) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const uint32_t rows = ((n + 31) / 32 + nwarp - 1) / nwarp;            // rows of 32 per warp
-    const uint32_t base = warp * rows * 32;
-    T carry = 0;
-    // two rows at a time: their shuffle scans are independent chains the scheduler interleaves.  More does not help: the 32 warps of the
-    // block share ONE shuffle unit (32 lanes per clock), so 313 rows x 5 steps x 2 SHFL (u64) = 3 100 clocks is the floor of this
-    // formulation; eight rows at a time was SLOWER (9 400 vs 6 600 clocks: the padding rows of the last group still shuffle, and the
-    // 64-register cap of a 1 024-thread block spills), profiles/r2_head_clocks_v2.jsonl / _v3.jsonl
-    constexpr int G = 2;
-    for (uint32_t r0 = 0; r0 < rows; r0 += G) {
-        T v[G], incl[G];
+// exclusive prefix sum of x[0..n) in shared memory, x[n] = total.  Raking form: thread t owns the K consecutive elements from t*K
+// (K = ceil(n / threads) made odd, so the thread stride is conflict-free for 32- and 64-bit words alike), sums them in registers, the
+// block scans the 1 024 thread totals with one warp scan per warp plus one over the 32 warp totals, and every thread writes its
+// running prefix back: one load pass, one store pass, 5 shuffle steps per WARP.  The row-wise form it replaces (a 5-step shuffle scan
+// per ROW of 32, 313 rows) sat on the block's one shuffle unit: 6 200 clocks for the u64 scan and 3 500 for the u32 one
+// (profiles/r2h_head_clocks_single_walk.jsonl).
+template <class T, int MAXPT> __device__ __forceinline__ void smem_exclusive_scan(T* x, uint32_t n, T* warp_tot) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const uint32_t K = ((n + blockDim.x - 1) / blockDim.x) | 1u;           // <= MAXPT: the caller's n <= MAXPT * threads, MAXPT odd
+    const uint32_t i0 = tid * K;
+    T v[MAXPT];
+    T tot = 0;
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            const uint32_t i = base + (r0 + g) * 32 + lane;
-            v[g] = (r0 + g < rows && i < n) ? x[i] : (T)0;
-            incl[g] = v[g];
-        }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                const T o = __shfl_up_sync(B2_FULL_MASK, incl[g], d);
-                if ((int)lane >= d) incl[g] += o;
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            const uint32_t i = base + (r0 + g) * 32 + lane;
-            const T tot = __shfl_sync(B2_FULL_MASK, incl[g], 31);
-            if (r0 + g < rows && i < n) x[i] = carry + incl[g] - v[g];   // exclusive within the warp's range
-            carry += tot;
-        }
+    for (int j = 0; j < MAXPT; j++) {
+        const uint32_t i = i0 + j;
+        v[j] = ((uint32_t)j < K && i < n) ? x[i] : (T)0;
+        tot += v[j];
     }
-    if (lane == 0) warp_tot[warp] = carry;
+    T incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const T o = __shfl_up_sync(B2_FULL_MASK, incl, d);
+        if ((int)lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
     if (warp == 0) {
         const T w = lane < nwarp ? warp_tot[lane] : (T)0;
@@ -841,12 +830,13 @@ template <class T> __device__ __forceinline__ void smem_exclusive_scan(T* x, uin
         if (lane == 31) x[n] = wi;                                          // grand total
     }
     __syncthreads();
-    const T off = warp_tot[warp];
-    if (off != 0)
-        for (uint32_t r = 0; r < rows; r++) {
-            const uint32_t i = base + r * 32 + lane;
-            if (i < n) x[i] += off;
-        }
+    T run = warp_tot[warp] + incl - tot;                                    // exclusive prefix of the thread's first element
+#pragma unroll
+    for (int j = 0; j < MAXPT; j++) {
+        const uint32_t i = i0 + j;
+        if ((uint32_t)j < K && i < n) x[i] = run;
+        run += v[j];
+    }
     __syncthreads();
 }
 __device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsigned long long* smem_u64, uint32_t* host_out, uint32_t host_seq) {
@@ -885,7 +875,7 @@ __device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsign
     if (tid == 0) mark[n] = 0;
     __syncthreads();
     B2_TREE_STAMP(1);
-    smem_exclusive_scan(W, n, warp_tot);
+    smem_exclusive_scan<unsigned long long, MAXPT>(W, n, warp_tot);
     B2_TREE_STAMP(2);
     {
         unsigned long long wreg[MAXPT];
@@ -944,9 +934,13 @@ __device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsign
         if (tid == 0) n_hard = 0;
         __syncthreads();
         const uint32_t lane = tid & 31;
-#pragma unroll 1
-        for (uint32_t p0 = 0; p0 < n; p0 += T) {
-            const uint32_t p = p0 + tid;
+        // all of a thread's tests first (their loads overlap), ONE reservation per warp: a reservation per trip was 320 returning
+        // atomics on one shared word, each trip waiting for its own
+        unsigned hm[MAXPT];
+        uint32_t wcount = 0;
+#pragma unroll
+        for (int j = 0; j < MAXPT; j++) {
+            const uint32_t p = tid + j * T;
             bool hard = false;
             if (p < n) {
                 const uint32_t sk = sz[p];
@@ -955,13 +949,19 @@ __device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsign
                     hard = !(B2_SZ(s1) + 1 == B2_SZ(sk) && B2_KEEP(sk) && B2_KEEP(s1));      // not "one child, kept": needs the loops
                 }
             }
-            const unsigned m = __ballot_sync(B2_FULL_MASK, hard);
-            uint32_t at = 0;
-            if (lane == 0 && m) at = atomicAdd(&n_hard, (uint32_t)__popc(m));
-            at = __shfl_sync(B2_FULL_MASK, at, 0);
-            if (hard) list[at + __popc(m & ((1u << lane) - 1u))] = p;
+            hm[j] = __ballot_sync(B2_FULL_MASK, hard);
+            wcount += __popc(hm[j]);
+        }
+        uint32_t at = 0;
+        if (lane == 0 && wcount) at = atomicAdd(&n_hard, wcount);
+        at = __shfl_sync(B2_FULL_MASK, at, 0);
+#pragma unroll
+        for (int j = 0; j < MAXPT; j++) {
+            if ((hm[j] >> lane) & 1u) list[at + __popc(hm[j] & ((1u << lane) - 1u))] = tid + j * T;
+            at += __popc(hm[j]);
         }
         __syncthreads();
+        B2_TREE_STAMP(8);
         const uint32_t nh = n_hard;
         for (uint32_t i = tid; i < nh; i += T) {
             const uint32_t p = list[i];
@@ -975,7 +975,7 @@ __device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsign
     }
     __syncthreads();
     B2_TREE_STAMP(5);
-    smem_exclusive_scan(mark, n, warp_tot32);
+    smem_exclusive_scan<uint32_t, MAXPT>(mark, n, warp_tot32);
     B2_TREE_STAMP(6);
     const uint32_t base = mark[jp + 1];
     const uint32_t jend = jp + B2_SZ(sz[jp]);

@@ -28,5 +28,6 @@ tree = [int(c[i + 1] - c[i]) for i in range(7)] + [int(c[15] - c[7])]
 votes = [int(c[17] - c[16]), int(c[18] - c[17]), int(c[19] - c[18])]
 print(json.dumps({"fused": os.environ.get("B2_HEAD_FUSED", "1"), "head": h, "p50_us": lat[150], "p10_us": lat[30], "p99_us": lat[296],
                   "tree_phase_clocks": dict(zip(["stage", "scan1", "weights", "store", "mark", "scan2", "find", "publish"], tree)),
+                  "mark_list_build_clocks": int(c[8] - c[4]) if c[8] else None,
                   "tree_total_clocks": int(c[15] - c[0]), "votes_cta0_clocks": dict(zip(["zero_bins", "scatter", "flush"], votes)),
                   "votes_start_to_tree_end_clocks": int(c[15] - c[16])}))
