@@ -839,11 +839,14 @@ template <class T, int MAXPT> __device__ __forceinline__ void smem_exclusive_sca
     }
     __syncthreads();
 }
-__device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsigned long long* smem_u64, uint32_t* host_out, uint32_t host_seq) {
-    __shared__ unsigned long long warp_tot[32];
-    __shared__ uint32_t warp_tot32[32];
-    __shared__ uint32_t head_pos, n_hard;
-    constexpr int MAXPT = 15;                                               // n <= 15 * 1024 (b2_head_from_votes_dev's use_smem test)
+// MAXPT = elements per thread the unrolled loops are built for (odd, n <= MAXPT * 1024).  The block's 32 warps share four issue
+// slots, so the phase times are instruction counts: the 15-trip form spends a third of its instructions on predicated-off trips
+// when n = 10 000 needs 10 (11 in the scans), hence the two instantiations behind ghost_tree_smem().
+template <int MAXPT>
+__device__ __forceinline__ void ghost_tree_smem_t(const ghost_tree_args& A, unsigned long long* smem_u64, uint32_t* host_out, uint32_t host_seq,
+                                               unsigned long long* warp_tot, uint32_t* warp_tot32, uint32_t* cells) {
+    uint32_t& head_pos = cells[0];
+    uint32_t& n_hard = cells[1];
     const uint32_t n = A.n, tid = threadIdx.x, T = blockDim.x;
     B2_TREE_STAMP(0);
     unsigned long long* W = smem_u64;                                       // n+1: votes -> prefix sums -> weights
@@ -997,6 +1000,13 @@ __device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsign
             *reinterpret_cast<volatile unsigned long long*>(host_out) = (unsigned long long)h | ((unsigned long long)host_seq << 32);
     }
     B2_TREE_STAMP(15);
+}
+__device__ __forceinline__ void ghost_tree_smem(const ghost_tree_args& A, unsigned long long* smem_u64, uint32_t* host_out, uint32_t host_seq) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ uint32_t warp_tot32[32];
+    __shared__ uint32_t cells[2];                                           // head position, length of the work list
+    if (A.n <= 11u * blockDim.x) ghost_tree_smem_t<11>(A, smem_u64, host_out, host_seq, warp_tot, warp_tot32, cells);
+    else ghost_tree_smem_t<15>(A, smem_u64, host_out, host_seq, warp_tot, warp_tot32, cells);      // n <= 15 * 1024: b2_head_from_votes_dev's use_smem test
 }
 
 __global__ void __launch_bounds__(1024) k_ghost_tree(ghost_tree_args A) {
